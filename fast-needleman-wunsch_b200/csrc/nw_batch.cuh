@@ -1,0 +1,106 @@
+// nw_batch.cuh -- batch of independent pairs (BASELINE.json configs[4]): one warp per pair, no HBM boundary traffic.
+//
+// Same recurrence and the same G = H + i + j change of variable as nw_kernels.cuh (reference arithmetic:
+// src/serial/serial.cpp:12-31).  A pair of len2 rows is covered by ceil(len2 / (32*R)) row strips handled one after
+// the other by the SAME warp; the boundary row between two strips of a pair lives in a per-warp scratch row
+// (L2-resident, updated in place).  For the headline shape (1000 x 1000, R = 32) there is exactly one strip and the
+// only global traffic is the 2 x 1000 sequence bytes in and one int32 score out.
+#pragma once
+#include "nw_kernels.cuh"
+
+namespace nw {
+
+struct BatchParams {
+    const uint8_t* S1;      // npairs x len1 bytes (columns)
+    const uint8_t* S2;      // npairs x len2 bytes (rows)
+    int32_t* scores;        // npairs
+    int32_t* scratch;       // total_warps x scratch_pitch ints (only used when nstrips > 1)
+    long long npairs;
+    long long scratch_pitch;
+    int len1, len2;
+    int nstrips, pad_top;
+    int generic;
+    uint8_t code[256];      // 4-letter path: byte value -> 0..3
+};
+
+template <bool GENERIC>
+__device__ __forceinline__ uint32_t batch_col_operand(const uint8_t* s1, int c, int len1, const uint8_t* lut)
+{
+    if (c < 0 || c >= len1) return GENERIC ? 0x100u : 0x02020202u;
+    const uint32_t v = s1[c];
+    return GENERIC ? v : 0x02020202u + (1u << (8 * lut[v]));
+}
+
+template <int R, bool GENERIC>
+__global__ void __launch_bounds__(256) nw_batch_kernel(const BatchParams p)
+{
+    extern __shared__ uint32_t nw_smem[];
+    __shared__ uint8_t lut[256];
+    for (int x = threadIdx.x; x < 256; x += blockDim.x) lut[x] = p.code[x];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint32_t* W = nw_smem + warp * SMEM_WORDS_PER_WARP;
+    int* sin = (int*)(W + 64);
+    int* sout = sin + 32;
+    const uint32_t* Wl = W + 32 - lane;
+    const long long gw = (long long)blockIdx.x * nwarps + warp, nw_total = (long long)gridDim.x * nwarps;
+    int32_t* scratch = p.scratch + gw * p.scratch_pitch;
+    const int ncols = p.len1;
+    const int nblocks = (ncols + 62) >> 5;
+    int32_t* const nofull_t[1] = {nullptr};
+    const int nofull_h[1] = {0};
+
+    for (long long pair = gw; pair < p.npairs; pair += nw_total) {
+        const uint8_t* s1 = p.S1 + pair * p.len1;
+        const uint8_t* s2 = p.S2 + pair * p.len2;
+        int h[R];
+        for (int s = 0; s < p.nstrips; ++s) {
+            RowOperands<R, GENERIC> ro;
+            const int k0 = s * 32 * R + lane * R - p.pad_top;      // index into s2 of this lane's first row
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int k = k0 + r;
+                uint32_t v;
+                if (k >= 0) v = GENERIC ? (uint32_t)s2[k] : (0x5550u | lut[s2[k]]);
+                else v = GENERIC ? 0x200u : 0xCCCCu;
+                ro.sel[r] = v;
+                if (GENERIC) ro.wx[GENERIC ? r : 0] = (v == 0x200u) ? -1 : 2;
+            }
+            int dprev = 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) h[r] = 0;
+
+            W[lane] = GENERIC ? 0x100u : 0x02020202u;
+            W[lane + 32] = batch_col_operand<GENERIC>(s1, lane, ncols, lut);
+            uint32_t wnext = batch_col_operand<GENERIC>(s1, 32 + lane, ncols, lut);
+            int pre = 0;
+            if (s > 0 && lane < ncols) pre = scratch[lane];
+            for (int b = 0; b < nblocks; ++b) {
+                const int cb = b << 5;
+                if (b > 0) {
+                    W[lane] = W[lane + 32];
+                    W[lane + 32] = wnext;
+                    wnext = batch_col_operand<GENERIC>(s1, cb + 32 + lane, ncols, lut);
+                }
+                sin[lane] = pre;
+                if (s > 0 && cb + 32 + lane < ncols) pre = scratch[cb + 32 + lane];
+                __syncwarp();
+                if (cb >= 31 && cb + 31 < ncols)
+                    sweep32<R, GENERIC, false, false>(h, dprev, ro, Wl, sin, sout, lane, cb, ncols, nofull_t, nofull_h);
+                else
+                    sweep32<R, GENERIC, false, true>(h, dprev, ro, Wl, sin, sout, lane, cb, ncols, nofull_t, nofull_h);
+                __syncwarp();
+                if (s + 1 < p.nstrips) {
+                    const int oc = cb - 31 + lane;
+                    if (oc >= 0 && oc < ncols) scratch[oc] = sout[lane];
+                }
+            }
+            __syncwarp();
+        }
+        // lane 31 holds G[len2][len1] (or 0 when there is no interior); H = G - i - j
+        if (lane == 31) p.scores[pair] = ((ncols > 0 && p.nstrips > 0) ? h[R - 1] : 0) - p.len1 - p.len2;
+    }
+}
+
+}  // namespace nw

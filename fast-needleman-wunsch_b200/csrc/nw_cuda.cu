@@ -1,0 +1,1017 @@
+// nw_cuda.cu -- libnw_cuda.so: the C ABI declared in include/nw_cuda.h over the sm_100a kernels of nw_kernels.cuh.
+//
+// Replaces, for the reference's callers, the body of
+//     void needlemanWunsch(dnaArray s1, dnaArray s2, int* t)            (reference: src/serial/serial.cpp:4-36)
+// and, for multi-GPU runs, the column-strip pipeline of src/mpi/mpi-vert.cpp:17-105 / mpi-vert-driver.cpp:35-38.
+// There is no CPU fallback in this file: every compute entry point needs a CUDA device and fails with NW_ERR_CUDA
+// (message in nw_cuda_last_error()) when there is none.
+#include "../../include/nw_cuda.h"
+#include "nw_kernels.cuh"
+#include "nw_batch.cuh"
+
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(NW_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct DeviceState {
+    bool inited = false;
+    int sm_count = 0;
+    cudaDeviceProp prop;
+};
+std::mutex g_mu;
+DeviceState g_dev[64];
+
+int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// ---- kernel dispatch ---------------------------------------------------------------------------------------------
+typedef void (*StripKernel)(const nw::StripParams);
+
+template <int R>
+StripKernel strip_kernel_r(bool generic, bool full)
+{
+    if (generic) return full ? nw::nw_strip_kernel<R, true, true> : nw::nw_strip_kernel<R, true, false>;
+    return full ? nw::nw_strip_kernel<R, false, true> : nw::nw_strip_kernel<R, false, false>;
+}
+StripKernel strip_kernel(int R, bool generic, bool full)
+{
+    switch (R) {
+    case 1: return strip_kernel_r<1>(generic, full);
+    case 2: return strip_kernel_r<2>(generic, full);
+    case 4: return strip_kernel_r<4>(generic, full);
+    case 8: return strip_kernel_r<8>(generic, full);
+    default: return nullptr;
+    }
+}
+
+typedef void (*BatchKernel)(const nw::BatchParams);
+BatchKernel batch_kernel(int R, bool generic)
+{
+    switch (R) {
+    case 4: return generic ? nw::nw_batch_kernel<4, true> : nw::nw_batch_kernel<4, false>;
+    case 8: return generic ? nw::nw_batch_kernel<8, true> : nw::nw_batch_kernel<8, false>;
+    case 16: return generic ? nw::nw_batch_kernel<16, true> : nw::nw_batch_kernel<16, false>;
+    case 32: return generic ? nw::nw_batch_kernel<32, true> : nw::nw_batch_kernel<32, false>;
+    default: return nullptr;
+    }
+}
+
+// byte value -> 0..3 when at most four distinct byte values occur; returns false otherwise (generic path)
+bool build_code(const bool seen[256], uint8_t code[256])
+{
+    int n = 0;
+    memset(code, 0, 256);
+    for (int v = 0; v < 256; ++v)
+        if (seen[v]) {
+            if (n == 4) return false;
+            code[v] = (uint8_t)n++;
+        }
+    return true;
+}
+
+void bitmap_to_seen(const uint32_t bm[8], bool seen[256])
+{
+    for (int v = 0; v < 256; ++v) seen[v] = (bm[v >> 5] >> (v & 31)) & 1u;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+// plan
+// =====================================================================================================================
+struct nw_plan {
+    int device = 0;
+    int n1 = 0, n2 = 0, mode = 0, part = 0, nparts = 1;
+    int jstart = 0;       // global table column of this part's left boundary column
+    int ncols = 0;        // interior columns of this part
+    int R = 4, warps = 8, ctas = 0, nstrips = 0, pad_top = 0;
+    bool generic = false, uploaded = false;
+    int epoch = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // device memory
+    uint8_t *d_s1 = nullptr, *d_s2 = nullptr;
+    uint32_t *d_wq = nullptr, *d_rsel = nullptr, *d_bitmap = nullptr;
+    int2* d_brow = nullptr;
+    long long pitch = 0;
+    int2* d_mailbox = nullptr;       // 2 x mpitch tagged words: halo of parts > 0 (double-buffered by epoch parity)
+    int2* d_rcol_local = nullptr;    // 2 x mpitch: right column when nobody is connected on the right
+    long long mpitch = 0;
+    int2* rcol_target = nullptr;     // where the right column goes: d_rcol_local, or the right neighbour's mailbox
+    bool rcol_peer = false, halo_peer = false;
+    // the 64 bytes after a mailbox's two buffers hold its "consumed epoch" word, written by the consumer's finish
+    // kernel and polled by the producer (over NVLink when the producer is another GPU)
+    void* ipc_mailbox = nullptr;     // imported peer mappings (closed on destroy)
+    int32_t *d_table = nullptr, *d_dump = nullptr;
+    long long tpitch = 0;
+    int32_t *d_last_row = nullptr, *d_last_col = nullptr, *d_score = nullptr, *d_tmp_row = nullptr;
+    size_t smem = 0;
+    StripKernel kernel = nullptr;
+};
+
+static int ensure_device(int device)
+{
+    int n = 0;
+    CK(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n || device >= 64) return fail(NW_ERR_ARG, "device %d out of range (count %d)", device, n);
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceState& d = g_dev[device];
+    if (!d.inited) {
+        CK(cudaSetDevice(device));
+        CK(cudaFree(0));
+        CK(cudaGetDeviceProperties(&d.prop, device));
+        d.sm_count = d.prop.multiProcessorCount;
+        if (d.prop.major < 10)
+            return fail(NW_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                        d.prop.major, d.prop.minor);
+        d.inited = true;
+    }
+    return NW_OK;
+}
+
+extern "C" const char* nw_cuda_version(void) { return "nw_cuda 0.1 (sm_100a)"; }
+extern "C" const char* nw_cuda_last_error(void) { return g_err; }
+
+extern "C" int nw_cuda_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(NW_ERR_CUDA, "cudaGetDeviceCount -> %s", cudaGetErrorString(e));
+    return n;
+}
+
+extern "C" int nw_cuda_device_info(int device, char* name, int name_len, int* sm_count, int* sm_clock_mhz)
+{
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    const DeviceState& d = g_dev[device];
+    if (name && name_len > 0) snprintf(name, name_len, "%s", d.prop.name);
+    if (sm_count) *sm_count = d.sm_count;
+    if (sm_clock_mhz) {
+        int khz = 0;
+        CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+        *sm_clock_mhz = khz / 1000;
+    }
+    return NW_OK;
+}
+
+// ---- geometry -------------------------------------------------------------------------------------------------------
+// mpi-vert partition (src/mpi/mpi-vert-driver.cpp:35-36, src/mpi/mpi-vert.cpp:17):
+//   q = (n1+1)/P, start = q*p - (p>0), table columns owned = q + (p>0) + (p==P-1 ? (n1+1)%P : 0), first one = boundary.
+static void partition(int n1, int P, int p, int* jstart, int* ncols)
+{
+    const long long q = ((long long)n1 + 1) / P;
+    const long long start = q * p - (p > 0);
+    const long long owned = q + (p > 0) + ((p == P - 1) ? (((long long)n1 + 1) % P) : 0);
+    *jstart = (int)start;
+    *ncols = (int)(owned - 1);
+}
+
+static int choose_rows_per_lane(int n2, int ncols, int sm_count)
+{
+    // One warp keeps an SMSP's integer pipe busy once R >= ~4; below that the per-column overhead (shuffle, operand
+    // load) dominates, above it the wavefront has too few strips.  Strip start-up lag is ~48 columns per strip.
+    const int cand[4] = {8, 4, 2, 1};
+    double best = 1e300;
+    int bestR = 4;
+    const double slots = sm_count * 8.0;
+    for (int ci = 0; ci < 4; ++ci) {
+        const int R = cand[ci];
+        const double strips = (n2 + 32.0 * R - 1) / (32.0 * R);
+        const double tcol = 3.0 * R + 7.0;                                   // issue slots per column per warp
+        const double per_smsp = std::max(1.0, strips / (sm_count * 4.0));    // warps sharing one scheduler
+        const double rounds = std::max(1.0, strips / slots);
+        const double conc = std::min(strips, slots);
+        const double t = (ncols * rounds + conc * 48.0) * std::max(tcol * std::min(per_smsp, 2.0), 4.0 * R + 30.0);
+        if (t < best) { best = t; bestR = R; }
+    }
+    return bestR;
+}
+
+extern "C" int nw_plan_destroy(nw_plan* p)
+{
+    if (!p) return NW_OK;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->ipc_mailbox) cudaIpcCloseMemHandle(p->ipc_mailbox);
+    void* bufs[] = {p->d_s1, p->d_s2, p->d_wq, p->d_rsel, p->d_bitmap, p->d_brow, p->d_mailbox, p->d_rcol_local,
+                    p->d_table, p->d_dump, p->d_last_row, p->d_last_col, p->d_score, p->d_tmp_row};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return NW_OK;
+}
+
+static int plan_alloc(nw_plan* p, const nw_tuning* tuning)
+{
+    const DeviceState& d = g_dev[p->device];
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&p->ev0));
+    CK(cudaEventCreate(&p->ev1));
+
+    int R = tuning ? tuning->rows_per_lane : 0;
+    if (R == 0) R = env_int("NW_CUDA_R", 0);
+    if (R == 0) R = choose_rows_per_lane(p->n2, p->ncols, d.sm_count);
+    if (R != 1 && R != 2 && R != 4 && R != 8) return fail(NW_ERR_ARG, "rows_per_lane must be 1, 2, 4 or 8 (got %d)", R);
+    p->R = R;
+    int warps = tuning ? tuning->warps_per_cta : 0;
+    if (warps == 0) warps = env_int("NW_CUDA_WARPS", 0);
+    if (warps == 0) warps = 8;
+    if (warps < 1 || warps > 16) return fail(NW_ERR_ARG, "warps_per_cta must be in 1..16 (got %d)", warps);
+    p->warps = warps;
+    p->nstrips = (int)(((long long)p->n2 + 32LL * R - 1) / (32LL * R));
+    p->pad_top = p->nstrips * 32 * R - p->n2;
+
+    const int nc = p->ncols, n2 = p->n2;
+    CK(cudaMalloc(&p->d_s1, (size_t)std::max(nc, 1)));
+    CK(cudaMalloc(&p->d_s2, (size_t)std::max(n2, 1)));
+    CK(cudaMalloc(&p->d_wq, sizeof(uint32_t) * ((size_t)nc + 2 * nw::WQ_PAD)));
+    CK(cudaMalloc(&p->d_rsel, sizeof(uint32_t) * (size_t)std::max(p->nstrips * 32 * R, 1)));
+    CK(cudaMalloc(&p->d_bitmap, 8 * sizeof(uint32_t)));
+    p->pitch = ((long long)nc + 1 + 15) & ~15LL;
+    CK(cudaMalloc(&p->d_brow, sizeof(int2) * (size_t)p->pitch * (size_t)std::max(p->nstrips, 1)));
+    CK(cudaMemset(p->d_brow, 0, sizeof(int2) * (size_t)p->pitch * (size_t)std::max(p->nstrips, 1)));
+    p->mpitch = ((long long)n2 + 1 + 15) & ~15LL;
+    if (p->part > 0) {
+        CK(cudaMalloc(&p->d_mailbox, sizeof(int2) * 2 * (size_t)p->mpitch + 64));
+        CK(cudaMemset(p->d_mailbox, 0, sizeof(int2) * 2 * (size_t)p->mpitch + 64));
+    }
+    CK(cudaMalloc(&p->d_rcol_local, sizeof(int2) * 2 * (size_t)p->mpitch));
+    CK(cudaMemset(p->d_rcol_local, 0, sizeof(int2) * 2 * (size_t)p->mpitch));
+    p->rcol_target = p->d_rcol_local;
+    if (p->mode == NW_MODE_FULL) {
+        p->tpitch = (long long)nc + 1;
+        CK(cudaMalloc(&p->d_table, sizeof(int32_t) * (size_t)p->tpitch * ((size_t)n2 + 1)));
+        CK(cudaMalloc(&p->d_dump, sizeof(int32_t) * (size_t)p->tpitch));
+    }
+    CK(cudaMalloc(&p->d_last_row, sizeof(int32_t) * ((size_t)nc + 1)));
+    CK(cudaMalloc(&p->d_last_col, sizeof(int32_t) * ((size_t)n2 + 1)));
+    CK(cudaMalloc(&p->d_tmp_row, sizeof(int32_t) * ((size_t)nc + 1)));
+    CK(cudaMalloc(&p->d_score, 64));
+    p->smem = sizeof(uint32_t) * nw::SMEM_WORDS_PER_WARP * (size_t)p->warps;
+    return NW_OK;
+}
+
+static int plan_pick_kernel(nw_plan* p, const nw_tuning* tuning)
+{
+    const DeviceState& d = g_dev[p->device];
+    p->kernel = strip_kernel(p->R, p->generic, p->mode == NW_MODE_FULL);
+    if (!p->kernel) return fail(NW_ERR_ARG, "no kernel for R=%d", p->R);
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p->kernel, p->warps * 32, p->smem));
+    if (per_sm < 1) return fail(NW_ERR_CUDA, "strip kernel does not fit on an SM (warps=%d)", p->warps);
+    // ~8 resident warps per SM by default (2 per scheduler): enough to cover shuffle and L2 latency
+    int target_warps_per_sm = env_int("NW_CUDA_WARPS_PER_SM", 8);
+    int ctas_per_sm = std::max(1, std::min(per_sm, target_warps_per_sm / p->warps));
+    int cap = d.sm_count * ctas_per_sm;
+    int want = (p->nstrips + p->warps - 1) / p->warps;
+    int ctas = tuning ? tuning->ctas : 0;
+    if (ctas == 0) ctas = env_int("NW_CUDA_CTAS", 0);
+    if (ctas == 0) ctas = std::min(cap, want);
+    ctas = std::max(1, std::min(ctas, d.sm_count * per_sm));    // never more than can be co-resident
+    p->ctas = ctas;
+    return NW_OK;
+}
+
+extern "C" int nw_plan_create(nw_plan** out, int device, int32_t n1, int32_t n2, int mode, int part, int nparts,
+                              const nw_tuning* tuning)
+{
+    if (!out) return fail(NW_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (n1 < 0 || n2 < 0) return fail(NW_ERR_ARG, "negative sequence length (n1=%d, n2=%d)", n1, n2);
+    if (mode != NW_MODE_BOUNDARY && mode != NW_MODE_FULL) return fail(NW_ERR_ARG, "unknown mode %d", mode);
+    if (nparts < 1 || part < 0 || part >= nparts) return fail(NW_ERR_ARG, "bad part %d of %d", part, nparts);
+    if (nparts > 1 && ((long long)n1 + 1) / nparts < 2)
+        return fail(NW_ERR_ARG, "n1=%d is too short for %d column strips", n1, nparts);
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    nw_plan* p = new (std::nothrow) nw_plan;
+    if (!p) return fail(NW_ERR_CUDA, "out of host memory");
+    p->device = device;
+    p->n1 = n1;
+    p->n2 = n2;
+    p->mode = mode;
+    p->part = part;
+    p->nparts = nparts;
+    partition(n1, nparts, part, &p->jstart, &p->ncols);
+    rc = plan_alloc(p, tuning);
+    if (rc == NW_OK) rc = plan_pick_kernel(p, tuning);
+    if (rc != NW_OK) {
+        nw_plan_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return NW_OK;
+}
+
+static int plan_encode(nw_plan* p, const bool seen[256])
+{
+    nw::EncodeParams e;
+    p->generic = !build_code(seen, e.code);
+    if (env_int("NW_CUDA_GENERIC", 0)) p->generic = true;
+    e.s1 = p->d_s1;
+    e.s2 = p->d_s2;
+    e.wq_base = p->d_wq;
+    e.rsel = p->d_rsel;
+    e.ncols = p->ncols;
+    e.n2 = p->n2;
+    e.nrows_padded = p->nstrips * 32 * p->R;
+    e.pad_top = p->pad_top;
+    e.generic = p->generic ? 1 : 0;
+    nw::nw_encode_kernel<<<64, 256, 0, p->stream>>>(e);
+    CK(cudaGetLastError());
+    int rc = plan_pick_kernel(p, nullptr);
+    if (rc) return rc;
+    p->uploaded = true;
+    return NW_OK;
+}
+
+extern "C" int nw_plan_upload(nw_plan* p, const int8_t* s1, const int8_t* s2)
+{
+    if (!p) return fail(NW_ERR_ARG, "plan is NULL");
+    if ((p->n1 > 0 && !s1) || (p->n2 > 0 && !s2)) return fail(NW_ERR_ARG, "sequence pointer is NULL");
+    CK(cudaSetDevice(p->device));
+    // alphabet of BOTH full sequences, so that every part of a pipeline makes the same choice of path
+    bool seen[256] = {false};
+    const uint8_t* a = (const uint8_t*)s1;
+    const uint8_t* b = (const uint8_t*)s2;
+    for (int i = 0; i < p->n1; ++i) seen[a[i]] = true;
+    for (int i = 0; i < p->n2; ++i) seen[b[i]] = true;
+    if (p->ncols > 0) CK(cudaMemcpyAsync(p->d_s1, a + p->jstart, (size_t)p->ncols, cudaMemcpyHostToDevice, p->stream));
+    if (p->n2 > 0) CK(cudaMemcpyAsync(p->d_s2, b, (size_t)p->n2, cudaMemcpyHostToDevice, p->stream));
+    return plan_encode(p, seen);
+}
+
+extern "C" int nw_plan_upload_device(nw_plan* p, const int8_t* d_s1, const int8_t* d_s2)
+{
+    if (!p) return fail(NW_ERR_ARG, "plan is NULL");
+    if ((p->n1 > 0 && !d_s1) || (p->n2 > 0 && !d_s2)) return fail(NW_ERR_ARG, "sequence pointer is NULL");
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemsetAsync(p->d_bitmap, 0, 8 * sizeof(uint32_t), p->stream));
+    if (p->n1 > 0) nw::nw_presence_kernel<<<32, 256, 0, p->stream>>>((const uint8_t*)d_s1, p->n1, p->d_bitmap);
+    if (p->n2 > 0) nw::nw_presence_kernel<<<32, 256, 0, p->stream>>>((const uint8_t*)d_s2, p->n2, p->d_bitmap);
+    CK(cudaGetLastError());
+    uint32_t bm[8];
+    CK(cudaMemcpyAsync(bm, p->d_bitmap, sizeof bm, cudaMemcpyDeviceToHost, p->stream));
+    if (p->ncols > 0)
+        CK(cudaMemcpyAsync(p->d_s1, (const uint8_t*)d_s1 + p->jstart, (size_t)p->ncols, cudaMemcpyDeviceToDevice, p->stream));
+    if (p->n2 > 0) CK(cudaMemcpyAsync(p->d_s2, d_s2, (size_t)p->n2, cudaMemcpyDeviceToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    bool seen[256];
+    bitmap_to_seen(bm, seen);
+    return plan_encode(p, seen);
+}
+
+// ---- pipeline wiring ----------------------------------------------------------------------------------------------------
+extern "C" int nw_plan_connect(nw_plan* left, nw_plan* right)
+{
+    if (!left || !right) return fail(NW_ERR_ARG, "plan is NULL");
+    if (left->nparts != right->nparts || right->part != left->part + 1 || left->n1 != right->n1 || left->n2 != right->n2)
+        return fail(NW_ERR_ARG, "plans are not adjacent parts of the same pipeline");
+    if (left->R != right->R) return fail(NW_ERR_ARG, "adjacent parts must use the same rows_per_lane");
+    if (left->device != right->device) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, left->device, right->device));
+        if (!can) return fail(NW_ERR_UNSUPPORTED, "device %d cannot access device %d", left->device, right->device);
+        CK(cudaSetDevice(left->device));
+        cudaError_t e = cudaDeviceEnablePeerAccess(right->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+        cudaGetLastError();
+        CK(cudaSetDevice(right->device));
+        e = cudaDeviceEnablePeerAccess(left->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+        cudaGetLastError();
+        left->rcol_peer = true;
+        right->halo_peer = true;
+    }
+    left->rcol_target = right->d_mailbox;
+    return NW_OK;
+}
+
+// handle64 layout: [0..63] cudaIpcMemHandle_t of the consumer's mailbox
+extern "C" int nw_plan_export_mailbox(nw_plan* p, void* handle64)
+{
+    if (!p || !handle64) return fail(NW_ERR_ARG, "NULL argument");
+    if (p->part == 0) return fail(NW_ERR_STATE, "part 0 has no halo mailbox");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(cudaSetDevice(p->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, p->d_mailbox));
+    memcpy(handle64, &h, 64);
+    p->halo_peer = true;
+    return NW_OK;
+}
+
+extern "C" int nw_plan_import_mailbox(nw_plan* p, const void* handle64, int consumer_device)
+{
+    if (!p || !handle64) return fail(NW_ERR_ARG, "NULL argument");
+    if (p->part == p->nparts - 1) return fail(NW_ERR_STATE, "the last part has no right neighbour");
+    (void)consumer_device;
+    CK(cudaSetDevice(p->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    p->ipc_mailbox = ptr;
+    p->rcol_target = (int2*)ptr;
+    p->rcol_peer = true;
+    return NW_OK;
+}
+
+// ---- running ----------------------------------------------------------------------------------------------------------
+static int plan_enqueue(nw_plan* p)
+{
+    if (!p->uploaded) return fail(NW_ERR_STATE, "nw_plan_upload has not been called");
+    CK(cudaSetDevice(p->device));
+    p->epoch += 1;
+    const int par = p->epoch & 1;
+    const int2* halo = (p->part > 0) ? p->d_mailbox + (long long)par * p->mpitch : nullptr;
+    int2* rcol = p->rcol_target + (long long)par * p->mpitch;
+    const bool have_cells = p->ncols > 0 && p->n2 > 0;
+    if (p->mode == NW_MODE_FULL) {
+        nw::nw_table_row0_kernel<<<64, 256, 0, p->stream>>>(p->d_table, p->ncols, p->jstart);
+        CK(cudaGetLastError());
+        if (!have_cells && p->n2 > 0) {   // no interior column: the table is just the boundary column
+            if (halo) return fail(NW_ERR_UNSUPPORTED, "full-table part without interior columns");
+            nw::nw_table_col0_kernel<<<64, 256, 0, p->stream>>>(p->d_table, p->tpitch, p->n2);
+            CK(cudaGetLastError());
+        }
+    }
+    if (have_cells) {
+        nw::StripParams sp;
+        sp.wq = p->d_wq + nw::WQ_PAD;
+        sp.rsel = p->d_rsel;
+        sp.brow = p->d_brow;
+        sp.pitch = p->pitch;
+        sp.halo = halo;
+        sp.rcol = rcol;
+        sp.table = p->d_table;
+        sp.tpitch = p->tpitch;
+        sp.dump = p->d_dump;
+        sp.ncols = p->ncols;
+        sp.n2 = p->n2;
+        sp.nstrips = p->nstrips;
+        sp.pad_top = p->pad_top;
+        sp.jstart = p->jstart;
+        sp.epoch = p->epoch;
+        sp.halo_sys = p->halo_peer ? 1 : 0;
+        sp.rcol_sys = p->rcol_peer ? 1 : 0;
+        sp.ack_in = (p->rcol_target != p->d_rcol_local) ? (const int*)(p->rcol_target + 2 * p->mpitch) : nullptr;
+        void* args[] = {&sp};
+        CK(cudaLaunchCooperativeKernel((const void*)p->kernel, dim3(p->ctas), dim3(p->warps * 32), args, p->smem, p->stream));
+    }
+    {
+        const int2* brow_last = (p->n2 > 0 && have_cells) ? p->d_brow + (long long)(p->nstrips - 1) * p->pitch : nullptr;
+        // n2 > 0 but no interior column: the last row is the single boundary cell; handled through rcol/halo == nullptr
+        const int2* rc = have_cells ? rcol : nullptr;
+        nw::nw_finish_kernel<<<64, 256, 0, p->stream>>>(brow_last, rc, halo, p->ncols, p->n2, p->jstart, p->d_last_row,
+                                                         p->d_last_col, p->d_score,
+                                                         p->d_mailbox ? (int*)(p->d_mailbox + 2 * p->mpitch) : nullptr, p->epoch);
+        CK(cudaGetLastError());
+    }
+    return NW_OK;
+}
+
+extern "C" int nw_plan_run(nw_plan* p)
+{
+    if (!p) return fail(NW_ERR_ARG, "plan is NULL");
+    CK(cudaSetDevice(p->device));
+    CK(cudaEventRecord(p->ev0, p->stream));
+    int rc = plan_enqueue(p);
+    if (rc) return rc;
+    CK(cudaEventRecord(p->ev1, p->stream));
+    return NW_OK;
+}
+
+extern "C" int nw_plan_sync(nw_plan* p)
+{
+    if (!p) return fail(NW_ERR_ARG, "plan is NULL");
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    return NW_OK;
+}
+
+extern "C" int nw_plan_time(nw_plan* p, int iters, float* ms_per_fill)
+{
+    if (!p || !ms_per_fill || iters < 1) return fail(NW_ERR_ARG, "bad argument");
+    if (p->nparts > 1) return fail(NW_ERR_STATE, "nw_plan_time is for single-part plans; time pipelines with nw_plan_run");
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaEventRecord(p->ev0, p->stream));
+    for (int i = 0; i < iters; ++i) {
+        int rc = plan_enqueue(p);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(p->ev1, p->stream));
+    CK(cudaEventSynchronize(p->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+    *ms_per_fill = ms / iters;
+    return NW_OK;
+}
+
+extern "C" int nw_plan_last_ms(nw_plan* p, float* ms)
+{
+    if (!p || !ms) return fail(NW_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(p->device));
+    CK(cudaEventSynchronize(p->ev1));
+    CK(cudaEventElapsedTime(ms, p->ev0, p->ev1));
+    return NW_OK;
+}
+
+extern "C" int nw_plan_launches_per_run(nw_plan* p, int* n)
+{
+    if (!p || !n) return fail(NW_ERR_ARG, "bad argument");
+    const bool have_cells = p->ncols > 0 && p->n2 > 0;
+    *n = (have_cells ? 1 : 0) + 1 + (p->mode == NW_MODE_FULL ? 1 + ((!have_cells && p->n2 > 0) ? 1 : 0) : 0);
+    return NW_OK;
+}
+
+// ---- results ------------------------------------------------------------------------------------------------------------
+extern "C" int nw_plan_score(nw_plan* p, int32_t* score)
+{
+    if (!p || !score) return fail(NW_ERR_ARG, "bad argument");
+    if (p->epoch == 0) return fail(NW_ERR_STATE, "no fill has been run");
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpyAsync(score, p->d_score, sizeof(int32_t), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return NW_OK;
+}
+
+extern "C" int nw_plan_last_row(nw_plan* p, int32_t* last_row)
+{
+    if (!p || !last_row) return fail(NW_ERR_ARG, "bad argument");
+    if (p->epoch == 0) return fail(NW_ERR_STATE, "no fill has been run");
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpyAsync(last_row, p->d_last_row, sizeof(int32_t) * ((size_t)p->ncols + 1), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return NW_OK;
+}
+
+extern "C" int nw_plan_last_col(nw_plan* p, int32_t* last_col)
+{
+    if (!p || !last_col) return fail(NW_ERR_ARG, "bad argument");
+    if (p->epoch == 0) return fail(NW_ERR_STATE, "no fill has been run");
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpyAsync(last_col, p->d_last_col, sizeof(int32_t) * ((size_t)p->n2 + 1), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return NW_OK;
+}
+
+extern "C" int nw_plan_table_to_host(nw_plan* p, int32_t* table)
+{
+    if (!p || !table) return fail(NW_ERR_ARG, "bad argument");
+    if (p->mode != NW_MODE_FULL) return fail(NW_ERR_STATE, "plan is not in full-table mode");
+    if (p->epoch == 0) return fail(NW_ERR_STATE, "no fill has been run");
+    CK(cudaSetDevice(p->device));
+    const size_t host_pitch = sizeof(int32_t) * ((size_t)p->n1 + 1);
+    // parts > 0 own their halo column too, but it is the left neighbour's last column: copy interior columns only
+    const int skip = (p->part > 0) ? 1 : 0;
+    const size_t width = sizeof(int32_t) * ((size_t)p->ncols + 1 - skip);
+    if (width == 0) return NW_OK;
+    if (p->nparts == 1) {
+        CK(cudaMemcpyAsync(table, p->d_table, host_pitch * ((size_t)p->n2 + 1), cudaMemcpyDeviceToHost, p->stream));
+    } else {
+        CK(cudaMemcpy2DAsync(table + p->jstart + skip, host_pitch, p->d_table + skip, sizeof(int32_t) * (size_t)p->tpitch,
+                             width, (size_t)p->n2 + 1, cudaMemcpyDeviceToHost, p->stream));
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    return NW_OK;
+}
+
+extern "C" int nw_plan_table_device(nw_plan* p, int32_t** d_table, int64_t* pitch)
+{
+    if (!p || !d_table || !pitch) return fail(NW_ERR_ARG, "bad argument");
+    if (p->mode != NW_MODE_FULL) return fail(NW_ERR_STATE, "plan is not in full-table mode");
+    *d_table = p->d_table;
+    *pitch = p->tpitch;
+    return NW_OK;
+}
+
+extern "C" int nw_plan_strip_info(nw_plan* p, int* nstrips, int* strip_rows, int* rows_per_lane, int* warps, int* ctas)
+{
+    if (!p) return fail(NW_ERR_ARG, "plan is NULL");
+    if (nstrips) *nstrips = p->nstrips;
+    if (strip_rows) *strip_rows = 32 * p->R;
+    if (rows_per_lane) *rows_per_lane = p->R;
+    if (warps) *warps = p->warps;
+    if (ctas) *ctas = p->ctas;
+    return NW_OK;
+}
+
+extern "C" int nw_plan_strip_row(nw_plan* p, int strip, int32_t* row)
+{
+    if (!p || !row) return fail(NW_ERR_ARG, "bad argument");
+    if (strip < 0 || strip >= p->nstrips) return fail(NW_ERR_ARG, "strip %d out of range (%d strips)", strip, p->nstrips);
+    if (p->epoch == 0) return fail(NW_ERR_STATE, "no fill has been run");
+    if (p->ncols == 0) return fail(NW_ERR_STATE, "part has no interior columns");
+    CK(cudaSetDevice(p->device));
+    const int row_i = p->n2 - (p->nstrips - 1 - strip) * 32 * p->R;
+    nw::nw_strip_row_kernel<<<64, 256, 0, p->stream>>>(p->d_brow + (long long)strip * p->pitch, p->ncols, row_i, p->jstart,
+                                                        p->d_tmp_row);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(row, p->d_tmp_row, sizeof(int32_t) * ((size_t)p->ncols + 1), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return NW_OK;
+}
+
+// =====================================================================================================================
+// one-shot entry points (host buffers)
+// =====================================================================================================================
+extern "C" int nw_cuda_init(int device)
+{
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    // warm-up: a tiny fill loads the module and creates the stream pools, so the reference driver's timed call
+    // (src/common/driver.cpp:26-30) does not pay for it
+    const int8_t a[40] = {1, 2, 3, 4, 1, 2, 3, 4, 1, 2, 3, 4, 1, 2, 3, 4, 1, 2, 3, 4,
+                          1, 2, 3, 4, 1, 2, 3, 4, 1, 2, 3, 4, 1, 2, 3, 4, 1, 2, 3, 4};
+    int32_t score = 0;
+    nw_plan* p = nullptr;
+    rc = nw_plan_create(&p, device, 40, 40, NW_MODE_BOUNDARY, 0, 1, nullptr);
+    if (rc == NW_OK) rc = nw_plan_upload(p, a, a);
+    if (rc == NW_OK) rc = nw_plan_run(p);
+    if (rc == NW_OK) rc = nw_plan_score(p, &score);
+    nw_plan_destroy(p);
+    if (rc == NW_OK && score != 40) return fail(NW_ERR_CUDA, "self-test failed: score %d, expected 40", score);
+    return rc;
+}
+
+static int run_pipeline(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int mode, int ngpus,
+                        int32_t* table, int32_t* last_row, int32_t* last_col, int32_t* score)
+{
+    if (ngpus < 1) return fail(NW_ERR_ARG, "ngpus must be >= 1");
+    if (ngpus > 1 && ((long long)n1 + 1) / ngpus < 2) ngpus = 1;     // too narrow to split
+    int ndev = nw_cuda_device_count();
+    if (ndev < 0) return ndev;
+    if (ndev < ngpus) return fail(NW_ERR_ARG, "%d GPUs requested, %d visible", ngpus, ndev);
+    std::vector<nw_plan*> plans((size_t)ngpus, nullptr);
+    int rc = NW_OK;
+    nw_tuning tune;
+    memset(&tune, 0, sizeof tune);
+    for (int g = 0; g < ngpus && rc == NW_OK; ++g) {
+        rc = nw_plan_create(&plans[g], g, n1, n2, mode, g, ngpus, g == 0 ? nullptr : &tune);
+        if (rc == NW_OK && g == 0) tune.rows_per_lane = plans[0]->R;     // all parts share the strip height
+    }
+    for (int g = 0; g + 1 < ngpus && rc == NW_OK; ++g) rc = nw_plan_connect(plans[g], plans[g + 1]);
+    for (int g = 0; g < ngpus && rc == NW_OK; ++g) rc = nw_plan_upload(plans[g], s1, s2);
+    for (int g = 0; g < ngpus && rc == NW_OK; ++g) rc = nw_plan_run(plans[g]);
+    for (int g = 0; g < ngpus && rc == NW_OK; ++g) rc = nw_plan_sync(plans[g]);
+    nw_plan* last = plans[(size_t)ngpus - 1];
+    if (rc == NW_OK && table && mode == NW_MODE_FULL)
+        for (int g = 0; g < ngpus && rc == NW_OK; ++g) rc = nw_plan_table_to_host(plans[g], table);
+    if (rc == NW_OK && score) rc = nw_plan_score(last, score);
+    if (rc == NW_OK && last_col) rc = nw_plan_last_col(last, last_col);
+    if (rc == NW_OK && last_row)
+        for (int g = 0; g < ngpus && rc == NW_OK; ++g) {
+            // part g's row covers global columns jstart .. jstart+ncols; column jstart of parts > 0 repeats the
+            // left neighbour's last column, so overlapping writes agree
+            std::vector<int32_t> tmp((size_t)plans[g]->ncols + 1);
+            rc = nw_plan_last_row(plans[g], tmp.data());
+            if (rc == NW_OK) memcpy(last_row + plans[g]->jstart, tmp.data(), sizeof(int32_t) * tmp.size());
+        }
+    char keep[512];
+    memcpy(keep, g_err, sizeof keep);
+    for (nw_plan* p : plans) nw_plan_destroy(p);
+    memcpy(g_err, keep, sizeof keep);
+    return rc;
+}
+
+extern "C" int nw_cuda_fill_ex(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int32_t* table, int mode,
+                               int ngpus)
+{
+    if (!table) return fail(NW_ERR_ARG, "table is NULL");
+    if (n1 < 0 || n2 < 0) return fail(NW_ERR_ARG, "negative sequence length");
+    if (mode == NW_MODE_FULL) return run_pipeline(s1, n1, s2, n2, mode, ngpus, table, nullptr, nullptr, nullptr);
+    if (mode != NW_MODE_BOUNDARY) return fail(NW_ERR_ARG, "unknown mode %d", mode);
+    int32_t score = 0;
+    int rc = run_pipeline(s1, n1, s2, n2, mode, ngpus, nullptr, nullptr, nullptr, &score);
+    if (rc == NW_OK) table[((long long)n1 + 1) * ((long long)n2 + 1) - 1] = score;     // what driver.cpp:35 reads
+    return rc;
+}
+
+extern "C" int nw_cuda_fill(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int32_t* table)
+{
+    int mode = NW_MODE_FULL;
+    const char* m = getenv("NW_CUDA_MODE");
+    if (m && *m) {
+        if (!strcmp(m, "boundary")) mode = NW_MODE_BOUNDARY;
+        else if (!strcmp(m, "full")) mode = NW_MODE_FULL;
+        else return fail(NW_ERR_ARG, "NW_CUDA_MODE must be 'full' or 'boundary' (got '%s')", m);
+    }
+    const int ngpus = env_int("NW_CUDA_GPUS", 1);
+    return nw_cuda_fill_ex(s1, n1, s2, n2, table, mode, ngpus);
+}
+
+extern "C" int nw_cuda_score(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int32_t* score)
+{
+    if (!score) return fail(NW_ERR_ARG, "score is NULL");
+    if (n1 < 0 || n2 < 0) return fail(NW_ERR_ARG, "negative sequence length");
+    return run_pipeline(s1, n1, s2, n2, NW_MODE_BOUNDARY, 1, nullptr, nullptr, nullptr, score);
+}
+
+extern "C" int nw_cuda_boundaries(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int32_t* last_row,
+                                  int32_t* last_col, int32_t* score)
+{
+    if (n1 < 0 || n2 < 0) return fail(NW_ERR_ARG, "negative sequence length");
+    return run_pipeline(s1, n1, s2, n2, NW_MODE_BOUNDARY, 1, nullptr, last_row, last_col, score);
+}
+
+// =====================================================================================================================
+// batch plans
+// =====================================================================================================================
+struct nw_batch {
+    int device = 0;
+    long long npairs = 0;
+    int len1 = 0, len2 = 0;
+    int R = 32, nstrips = 0, pad_top = 0, warps = 8, ctas = 0;
+    bool generic = false, uploaded = false, ran = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint8_t *d_S1 = nullptr, *d_S2 = nullptr;
+    const uint8_t *S1 = nullptr, *S2 = nullptr;    // what the kernel reads (own copies or caller's device arrays)
+    int32_t *d_scores = nullptr, *d_scratch = nullptr;
+    uint32_t* d_bitmap = nullptr;
+    long long scratch_pitch = 0;
+    uint8_t code[256];
+    BatchKernel kernel = nullptr;
+    size_t smem = 0;
+};
+
+extern "C" int nw_batch_destroy(nw_batch* b)
+{
+    if (!b) return NW_OK;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    void* bufs[] = {b->d_S1, b->d_S2, b->d_scores, b->d_scratch, b->d_bitmap};
+    for (void* x : bufs)
+        if (x) cudaFree(x);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+    return NW_OK;
+}
+
+static int batch_setup(nw_batch* b)
+{
+    const DeviceState& d = g_dev[b->device];
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&b->ev0));
+    CK(cudaEventCreate(&b->ev1));
+    int R = env_int("NW_CUDA_BATCH_R", 0);
+    if (R == 0) {
+        R = 32;
+        while (R > 4 && b->len2 <= 32 * (R / 2)) R /= 2;      // smallest strip that still covers the pair in one pass
+    }
+    if (R != 4 && R != 8 && R != 16 && R != 32) return fail(NW_ERR_ARG, "batch rows_per_lane must be 4, 8, 16 or 32");
+    b->R = R;
+    b->nstrips = (int)(((long long)b->len2 + 32LL * R - 1) / (32LL * R));
+    b->pad_top = b->nstrips * 32 * R - b->len2;
+    b->warps = 8;
+    b->smem = sizeof(uint32_t) * nw::SMEM_WORDS_PER_WARP * (size_t)b->warps;
+    CK(cudaMalloc(&b->d_scores, sizeof(int32_t) * (size_t)std::max<long long>(b->npairs, 1)));
+    CK(cudaMalloc(&b->d_bitmap, 8 * sizeof(uint32_t)));
+    b->kernel = batch_kernel(b->R, false);
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b->kernel, b->warps * 32, b->smem));
+    if (per_sm < 1) return fail(NW_ERR_CUDA, "batch kernel does not fit on an SM");
+    per_sm = std::min(per_sm, std::max(1, env_int("NW_CUDA_BATCH_CTAS_PER_SM", 2)));
+    long long want = (b->npairs + b->warps - 1) / b->warps;
+    b->ctas = (int)std::max<long long>(1, std::min<long long>(want, (long long)d.sm_count * per_sm));
+    b->scratch_pitch = ((long long)b->len1 + 63) & ~31LL;
+    if (b->nstrips > 1)
+        CK(cudaMalloc(&b->d_scratch, sizeof(int32_t) * (size_t)b->scratch_pitch * (size_t)b->ctas * (size_t)b->warps));
+    return NW_OK;
+}
+
+extern "C" int nw_batch_create(nw_batch** out, int device, int64_t npairs, int32_t len1, int32_t len2)
+{
+    if (!out) return fail(NW_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (npairs < 0 || len1 < 0 || len2 < 0) return fail(NW_ERR_ARG, "negative size");
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    nw_batch* b = new (std::nothrow) nw_batch;
+    if (!b) return fail(NW_ERR_CUDA, "out of host memory");
+    b->device = device;
+    b->npairs = npairs;
+    b->len1 = len1;
+    b->len2 = len2;
+    rc = batch_setup(b);
+    if (rc) {
+        nw_batch_destroy(b);
+        return rc;
+    }
+    *out = b;
+    return NW_OK;
+}
+
+static int batch_scan(nw_batch* b)
+{
+    // alphabet of the whole batch, on the device
+    CK(cudaMemsetAsync(b->d_bitmap, 0, 8 * sizeof(uint32_t), b->stream));
+    const long long t1 = b->npairs * b->len1, t2 = b->npairs * b->len2;
+    if (t1 > 0) nw::nw_presence_kernel64<<<296, 256, 0, b->stream>>>(b->S1, t1, b->d_bitmap);
+    if (t2 > 0) nw::nw_presence_kernel64<<<296, 256, 0, b->stream>>>(b->S2, t2, b->d_bitmap);
+    CK(cudaGetLastError());
+    uint32_t bm[8];
+    CK(cudaMemcpyAsync(bm, b->d_bitmap, sizeof bm, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    bool seen[256];
+    bitmap_to_seen(bm, seen);
+    b->generic = !build_code(seen, b->code);
+    if (env_int("NW_CUDA_GENERIC", 0)) b->generic = true;
+    b->kernel = batch_kernel(b->R, b->generic);
+    b->uploaded = true;
+    return NW_OK;
+}
+
+extern "C" int nw_batch_upload(nw_batch* b, const int8_t* S1, const int8_t* S2)
+{
+    if (!b) return fail(NW_ERR_ARG, "batch is NULL");
+    const size_t t1 = (size_t)b->npairs * (size_t)b->len1, t2 = (size_t)b->npairs * (size_t)b->len2;
+    if ((t1 && !S1) || (t2 && !S2)) return fail(NW_ERR_ARG, "sequence pointer is NULL");
+    CK(cudaSetDevice(b->device));
+    if (!b->d_S1) CK(cudaMalloc(&b->d_S1, std::max<size_t>(t1, 1)));
+    if (!b->d_S2) CK(cudaMalloc(&b->d_S2, std::max<size_t>(t2, 1)));
+    if (t1) CK(cudaMemcpyAsync(b->d_S1, S1, t1, cudaMemcpyHostToDevice, b->stream));
+    if (t2) CK(cudaMemcpyAsync(b->d_S2, S2, t2, cudaMemcpyHostToDevice, b->stream));
+    b->S1 = b->d_S1;
+    b->S2 = b->d_S2;
+    return batch_scan(b);
+}
+
+extern "C" int nw_batch_upload_device(nw_batch* b, const int8_t* d_S1, const int8_t* d_S2)
+{
+    if (!b) return fail(NW_ERR_ARG, "batch is NULL");
+    CK(cudaSetDevice(b->device));
+    b->S1 = (const uint8_t*)d_S1;      // borrowed: the caller keeps them alive
+    b->S2 = (const uint8_t*)d_S2;
+    return batch_scan(b);
+}
+
+static int batch_enqueue(nw_batch* b)
+{
+    if (!b->uploaded) return fail(NW_ERR_STATE, "nw_batch_upload has not been called");
+    if (b->npairs == 0) return NW_OK;
+    nw::BatchParams bp;
+    bp.S1 = b->S1;
+    bp.S2 = b->S2;
+    bp.scores = b->d_scores;
+    bp.scratch = b->d_scratch;
+    bp.npairs = b->npairs;
+    bp.scratch_pitch = b->scratch_pitch;
+    bp.len1 = b->len1;
+    bp.len2 = b->len2;
+    bp.nstrips = b->nstrips;
+    bp.pad_top = b->pad_top;
+    bp.generic = b->generic ? 1 : 0;
+    memcpy(bp.code, b->code, 256);
+    b->kernel<<<b->ctas, b->warps * 32, b->smem, b->stream>>>(bp);
+    CK(cudaGetLastError());
+    b->ran = true;
+    return NW_OK;
+}
+
+extern "C" int nw_batch_run(nw_batch* b)
+{
+    if (!b) return fail(NW_ERR_ARG, "batch is NULL");
+    CK(cudaSetDevice(b->device));
+    CK(cudaEventRecord(b->ev0, b->stream));
+    int rc = batch_enqueue(b);
+    if (rc) return rc;
+    CK(cudaEventRecord(b->ev1, b->stream));
+    return NW_OK;
+}
+
+extern "C" int nw_batch_sync(nw_batch* b)
+{
+    if (!b) return fail(NW_ERR_ARG, "batch is NULL");
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    return NW_OK;
+}
+
+extern "C" int nw_batch_time(nw_batch* b, int iters, float* ms_per_run)
+{
+    if (!b || !ms_per_run || iters < 1) return fail(NW_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    CK(cudaEventRecord(b->ev0, b->stream));
+    for (int i = 0; i < iters; ++i) {
+        int rc = batch_enqueue(b);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(b->ev1, b->stream));
+    CK(cudaEventSynchronize(b->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+    *ms_per_run = ms / iters;
+    return NW_OK;
+}
+
+extern "C" int nw_batch_scores(nw_batch* b, int32_t* scores)
+{
+    if (!b || (!scores && b->npairs)) return fail(NW_ERR_ARG, "bad argument");
+    if (!b->ran && b->npairs) return fail(NW_ERR_STATE, "no batch has been run");
+    CK(cudaSetDevice(b->device));
+    if (b->npairs)
+        CK(cudaMemcpyAsync(scores, b->d_scores, sizeof(int32_t) * (size_t)b->npairs, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return NW_OK;
+}
+
+extern "C" int nw_cuda_batch_scores(const int8_t* S1, const int8_t* S2, int64_t npairs, int32_t len1, int32_t len2,
+                                    int32_t* scores, int device)
+{
+    nw_batch* b = nullptr;
+    int rc = nw_batch_create(&b, device, npairs, len1, len2);
+    if (rc == NW_OK) rc = nw_batch_upload(b, S1, S2);
+    if (rc == NW_OK) rc = nw_batch_run(b);
+    if (rc == NW_OK) rc = nw_batch_scores(b, scores);
+    char keep[512];
+    memcpy(keep, g_err, sizeof keep);
+    nw_batch_destroy(b);
+    memcpy(g_err, keep, sizeof keep);
+    return rc;
+}
+
+// =====================================================================================================================
+// roofline support: integer / DPX pipe rate
+// =====================================================================================================================
+extern "C" int nw_cuda_dpx_peak(int device, double* giga_lane_ops_per_s, double* sm_clock_mhz)
+{
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    CK(cudaSetDevice(device));
+    const DeviceState& d = g_dev[device];
+    const int ctas = d.sm_count * 2, threads = 512, iters = 4096;
+    int* d_out = nullptr;
+    unsigned long long* d_clk = nullptr;
+    CK(cudaMalloc(&d_out, sizeof(int) * (size_t)ctas * threads));
+    CK(cudaMalloc(&d_clk, sizeof(unsigned long long) * 2 * (size_t)ctas));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(e0));
+        nw::nw_dpx_peak_kernel<<<ctas, threads>>>(d_out, d_clk, iters, rep);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaGetLastError());
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best_ms = std::min(best_ms, ms);
+    }
+    std::vector<unsigned long long> clk(2 * (size_t)ctas);
+    CK(cudaMemcpy(clk.data(), d_clk, sizeof(unsigned long long) * clk.size(), cudaMemcpyDeviceToHost));
+    double cyc = 0, ns = 0;
+    for (int i = 0; i < ctas; ++i) {
+        cyc += (double)clk[2 * i];
+        ns += (double)clk[2 * i + 1];
+    }
+    const double ops = (double)ctas * threads * (double)iters * nw::DPX_PEAK_OPS_PER_ITER;
+    if (giga_lane_ops_per_s) *giga_lane_ops_per_s = ops / (best_ms * 1e-3) / 1e9;
+    if (sm_clock_mhz) *sm_clock_mhz = (ns > 0) ? cyc / ns * 1e3 : 0.0;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    cudaFree(d_clk);
+    return NW_OK;
+}

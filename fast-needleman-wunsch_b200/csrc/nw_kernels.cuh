@@ -1,0 +1,425 @@
+// nw_kernels.cuh -- sm_100a device code of the Needleman-Wunsch wavefront fill.
+//
+// What is computed (reference: src/serial/serial.cpp:12-31, scoring src/common/needleman-wunsch.hpp:11-13):
+//     H[i][j] = max(H[i-1][j-1] + (s1[j-1]==s2[i-1]), H[i-1][j] - 1, H[i][j-1] - 1),  H[0][j] = -j, H[i][0] = -i
+// The kernels work on the shifted table  G[i][j] = H[i][j] + i + j  (exact integer change of variable):
+//     G[i][j] = max(G[i-1][j-1] + w, G[i-1][j], G[i][j-1]),  w = 2 + (s1[j-1]==s2[i-1]),  G[0][j] = G[i][0] = 0
+// so one cell is   w = PRMT(column word, row selector);  t = VIADDMNMX(diag, w, left);  G = VIMNMX(t, up)
+// -- three integer-pipe instructions, two of them Blackwell DPX (__viaddmax_s32 / max).  H = G - i - j is applied
+// only where cells leave the kernel (boundary rows/columns, table stores, the score).
+//
+// Decomposition: the table is cut into horizontal STRIPS of 32*R rows.  One warp owns a strip: lane L keeps R
+// consecutive rows in registers and sweeps the columns left to right, one column per step, lane L one column behind
+// lane L-1 (so a warp advances one anti-diagonal of 32 lane-blocks per step); the bottom cell of lane L-1 reaches lane
+// L with __shfl_up_sync.  The bottom row of a strip is written to HBM as "tagged" 64-bit words {epoch, G}; the warp
+// that owns the strip below polls those words (no flags, no fences: an aligned 8-byte store is single-copy atomic)
+// -- the GPU form of the reference's sentinel polling (src/sentinel/sentinel-otf-mt.cpp:44-51) and per-row progress
+// counters (src/idxarray/idxarray-mod-mt.cpp:54-79).  Strips are dealt round-robin to the warps of a persistent grid.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nw {
+
+constexpr int WQ_PAD = 64;          // the column operand array is addressable for col in [-WQ_PAD, ncols + WQ_PAD)
+constexpr unsigned FULL_MASK = 0xffffffffu;
+constexpr int SMEM_WORDS_PER_WARP = 128;   // 64 column operands + 32 top-row inputs + 32 bottom-row outputs
+
+// ---- tiny PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
+    return d;
+}
+// L1-bypassing loads/stores of tagged words {tag, value}
+__device__ __forceinline__ int2 ld_tagged_gpu(const int2* p)
+{
+    int2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int2 ld_tagged_sys(const int2* p)
+{
+    int2 v;
+    asm volatile("ld.relaxed.sys.global.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_tagged_gpu(int2* p, int tag, int val)
+{
+    asm volatile("st.relaxed.gpu.global.v2.s32 [%0], {%1,%2};" ::"l"(p), "r"(tag), "r"(val) : "memory");
+}
+__device__ __forceinline__ void st_tagged_sys(int2* p, int tag, int val)
+{
+    asm volatile("st.relaxed.sys.global.v2.s32 [%0], {%1,%2};" ::"l"(p), "r"(tag), "r"(val) : "memory");
+}
+
+// ---- kernel parameters ----------------------------------------------------------------------------------------
+struct StripParams {
+    const uint32_t* wq;     // column operand per interior column c (0-based), valid for c in [-WQ_PAD, ncols+WQ_PAD)
+                            //   4-letter path: bytes b=0..3 hold 2 + (code(s1[c]) == b);  generic path: the raw byte
+    const uint32_t* rsel;   // row operand per padded row q in [0, nstrips*32*R)
+                            //   4-letter path: PRMT selector (0x5550|code real rows, 0xCCCC virtual rows)
+                            //   generic path:  raw byte of s2 (real rows) or 0x200 (virtual rows)
+    int2* brow;             // nstrips x pitch tagged words: brow[s][j] = {epoch, G[last row of strip s][j]}, j=0..ncols
+    long long pitch;
+    const int2* halo;       // tagged left boundary column, indexed by table row i (1..n2); nullptr => all zero
+    int2* rcol;             // tagged right boundary column, indexed by table row i (1..n2); may be PEER memory
+    int32_t* table;         // FULL mode: rows 0..n2 x tpitch, this part's columns (local column 0 = left boundary)
+    long long tpitch;
+    int32_t* dump;          // FULL mode: scratch row (tpitch ints) that swallows the stores of virtual rows
+    int ncols;              // interior columns of this part
+    int n2;                 // table rows - 1
+    int nstrips;
+    int pad_top;            // virtual rows above table row 1: nstrips*32*R - n2
+    int jstart;             // global table column of this part's left boundary column
+    int epoch;              // tag of this run (never 0)
+    int halo_sys;           // halo written by a peer device: poll with system scope
+    int rcol_sys;           // rcol is peer memory: store with system scope
+    // back-pressure of a column-strip pipeline (mailboxes are double-buffered by epoch parity):
+    const int* ack_in;      // producer side: the consumer's "finished epoch" word (in the consumer's mailbox
+                            // allocation, possibly peer memory); the kernel waits for ack >= epoch - 2
+};
+
+// ---- the strip sweep -------------------------------------------------------------------------------------------
+template <int R, bool GENERIC>
+struct RowOperands {
+    uint32_t sel[R];
+    int wx[GENERIC ? R : 1];
+    __device__ __forceinline__ int weight(int r, uint32_t cop) const
+    {
+        if (GENERIC) return (sel[r] == cop) ? 3 : wx[r];
+        return (int)prmt(cop, 0x80u, sel[r]);
+    }
+};
+
+template <int R, bool GENERIC, bool FULL, bool PRED>
+__device__ __forceinline__ void sweep32(int (&h)[R], int& dprev, const RowOperands<R, GENERIC>& ro,
+                                        const uint32_t* __restrict__ Wl, const int* __restrict__ sin, int* sout,
+                                        const int lane, const int cb, const int ncols,
+                                        int32_t* const (&trow)[FULL ? R : 1], const int (&hoff)[FULL ? R : 1])
+{
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const uint32_t cop = Wl[k];
+        int up = __shfl_up_sync(FULL_MASK, h[R - 1], 1);
+        if (lane == 0) up = sin[k];
+        const int col = cb + k - lane;
+        if (!PRED || (col >= 0 && col < ncols)) {
+            int diag = dprev;
+            dprev = up;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int w = ro.weight(r, cop);
+                const int t = __viaddmax_s32(diag, w, h[r]);   // max(G[i-1][j-1] + w, G[i][j-1])
+                diag = h[r];
+                up = max(t, up);                               // ... , G[i-1][j])
+                h[r] = up;
+                if (FULL) trow[r][col + 1] = up - hoff[r] - col;   // H = G - i - j
+            }
+        }
+        if (lane == 31) sout[k] = h[R - 1];
+    }
+}
+
+template <int R, bool GENERIC, bool FULL>
+__device__ __forceinline__ void run_strip(const StripParams& p, const int s, const int lane, uint32_t* W, int* sin,
+                                          int* sout)
+{
+    constexpr int SH = 32 * R;
+    const int ncols = p.ncols;
+    const int q0 = s * SH + lane * R;            // first padded row of this lane
+    const int i0 = q0 - p.pad_top;               // table row just above this lane's first row (may be <= 0)
+
+    RowOperands<R, GENERIC> ro;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t v = p.rsel[q0 + r];
+        ro.sel[r] = v;
+        if (GENERIC) ro.wx[r] = (v == 0x200u) ? -1 : 2;
+    }
+
+    // left boundary column (G form): zero for a whole table, the neighbour's right column for a column strip
+    int h[R];
+    int dprev = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) h[r] = 0;
+    if (p.halo != nullptr) {
+#pragma unroll
+        for (int r = -1; r < R; ++r) {
+            const int i = i0 + 1 + r;
+            int v = 0;
+            if (i >= 1) {
+                int2 t;
+                do {
+                    t = p.halo_sys ? ld_tagged_sys(p.halo + i) : ld_tagged_gpu(p.halo + i);
+                    if (t.x != p.epoch) __nanosleep(200);
+                } while (t.x != p.epoch);
+                v = t.y;
+            }
+            if (r < 0) dprev = v; else h[r] = v;
+        }
+    }
+
+    int32_t* trow[FULL ? R : 1];
+    int hoff[FULL ? R : 1];
+    if (FULL) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = i0 + 1 + r;
+            trow[FULL ? r : 0] = (i >= 1) ? p.table + (long long)i * p.tpitch : p.dump;
+            hoff[FULL ? r : 0] = i + p.jstart + 1;     // H = G - i - (jstart + col + 1)
+            trow[FULL ? r : 0][0] = h[r] - i - p.jstart;   // left boundary column (serial.cpp:17 / mpi-vert.cpp:57-59)
+        }
+    }
+
+    int2* tout = p.brow + (long long)s * p.pitch;
+    const int2* tin = p.brow + (long long)(s - 1) * p.pitch;
+    if (lane == 31) st_tagged_gpu(tout, p.epoch, h[R - 1]);
+
+    // column operand window: W[0..63] holds columns [cb-32, cb+32) of the current 32-step block
+    const uint32_t* wq = p.wq;
+    W[lane] = wq[lane - 32];
+    W[lane + 32] = wq[lane];
+    uint32_t wnext = wq[32 + lane];
+    const uint32_t* Wl = W + 32 - lane;
+
+    // top boundary row: prefetched one block ahead
+    int2 pre = make_int2(0, 0);
+    if (s > 0 && lane < ncols) pre = ld_tagged_gpu(tin + lane + 1);
+    if (s == 0) sin[lane] = 0;
+
+    const int nblocks = (ncols + 31 + 31) >> 5;     // steps t = 0 .. ncols+30
+    for (int b = 0; b < nblocks; ++b) {
+        const int cb = b << 5;
+        if (b > 0) {
+            W[lane] = W[lane + 32];
+            W[lane + 32] = wnext;
+            int nc = cb + 32 + lane;
+            wnext = wq[nc < ncols + WQ_PAD ? nc : ncols + WQ_PAD - 1];
+        }
+        if (s > 0 && cb < ncols) {
+            const int col = cb + lane;
+            const bool need = col < ncols;
+            while (!__all_sync(FULL_MASK, !need || pre.x == p.epoch)) {
+                __nanosleep(100);
+                if (need && pre.x != p.epoch) pre = ld_tagged_gpu(tin + col + 1);
+            }
+            sin[lane] = pre.y;
+            if (col + 32 < ncols) pre = ld_tagged_gpu(tin + col + 33);
+        }
+        __syncwarp();
+        if (cb >= 31 && cb + 31 < ncols)
+            sweep32<R, GENERIC, FULL, false>(h, dprev, ro, Wl, sin, sout, lane, cb, ncols, trow, hoff);
+        else
+            sweep32<R, GENERIC, FULL, true>(h, dprev, ro, Wl, sin, sout, lane, cb, ncols, trow, hoff);
+        __syncwarp();
+        const int oc = cb - 31 + lane;               // column finished by lane 31 at step k = lane of this block
+        const int ov = sout[lane];
+        if (oc >= 0 && oc < ncols) st_tagged_gpu(tout + oc + 1, p.epoch, ov);
+    }
+
+    // right boundary column of this lane's rows
+    if (p.rcol != nullptr) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = i0 + 1 + r;
+            if (i >= 1) {
+                if (p.rcol_sys) st_tagged_sys(p.rcol + i, p.epoch, h[r]);
+                else st_tagged_gpu(p.rcol + i, p.epoch, h[r]);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <int R, bool GENERIC, bool FULL>
+__global__ void __launch_bounds__(512) nw_strip_kernel(const StripParams p)
+{
+    extern __shared__ uint32_t nw_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint32_t* W = nw_smem + warp * SMEM_WORDS_PER_WARP;
+    int* sin = (int*)(W + 64);
+    int* sout = sin + 32;
+    const int slot = blockIdx.x * nwarps + warp, nslots = gridDim.x * nwarps;
+    if (p.ack_in != nullptr) {          // do not overwrite a mailbox the consumer has not finished reading
+        if (threadIdx.x == 0) {
+            int a;
+            do {
+                asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(a) : "l"(p.ack_in) : "memory");
+                if (a < p.epoch - 2) __nanosleep(500);
+            } while (a < p.epoch - 2);
+        }
+        __syncthreads();
+    }
+    for (int s = slot; s < p.nstrips; s += nslots) run_strip<R, GENERIC, FULL>(p, s, lane, W, sin, sout);
+}
+
+// ---- preparation / finishing kernels (a few hundred KB of traffic; not on the critical path) --------------------
+// presence bitmap of the byte values that occur in a sequence
+__global__ void nw_presence_kernel(const uint8_t* s, int n, uint32_t* bitmap /*8 words*/)
+{
+    __shared__ uint32_t bm[8];
+    if (threadIdx.x < 8) bm[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t v = s[i];
+        atomicOr(&bm[v >> 5], 1u << (v & 31));
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && bm[threadIdx.x]) atomicOr(&bitmap[threadIdx.x], bm[threadIdx.x]);
+}
+
+struct EncodeParams {
+    const uint8_t* s1;      // this part's slice: ncols bytes
+    const uint8_t* s2;      // n2 bytes
+    uint32_t* wq_base;      // ncols + 2*WQ_PAD words (index c + WQ_PAD)
+    uint32_t* rsel;         // nrows_padded words
+    int ncols, n2, nrows_padded, pad_top;
+    int generic;
+    uint8_t code[256];      // 4-letter path: byte value -> 0..3
+};
+
+__global__ void nw_encode_kernel(const EncodeParams e)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int x = tid; x < e.ncols + 2 * WQ_PAD; x += nth) {
+        const int c = x - WQ_PAD;
+        uint32_t v;
+        if (c >= 0 && c < e.ncols) v = e.generic ? (uint32_t)e.s1[c] : 0x02020202u + (1u << (8 * e.code[e.s1[c]]));
+        else v = e.generic ? 0x100u : 0x02020202u;
+        e.wq_base[x] = v;
+    }
+    for (int q = tid; q < e.nrows_padded; q += nth) {
+        const int k = q - e.pad_top;     // index into s2
+        uint32_t v;
+        if (k >= 0) v = e.generic ? (uint32_t)e.s2[k] : (0x5550u | e.code[e.s2[k]]);
+        else v = e.generic ? 0x200u : 0xCCCCu;
+        e.rsel[q] = v;
+    }
+}
+
+// first row of a materialised table (reference: src/serial/serial.cpp:16, mpi-vert.cpp:20); the first column is
+// written by the strip kernel itself because in a pipeline it is the halo, which arrives while the kernel runs.
+__global__ void nw_table_row0_kernel(int32_t* table, int ncols, int jstart)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int j = tid; j <= ncols; j += nth) table[j] = -(jstart + j);
+}
+
+// boundary outputs in H form: last_row[j] = H[n2][jstart+j], last_col[i] = H[i][jstart+ncols].
+// brow_last == nullptr  <=> there are no interior cells (n2 == 0: the last row is the init row; ncols == 0: the part is
+// its boundary column only);  rcol == nullptr likewise: the last column is the left boundary (the halo, or H[i][0] = -i).
+__global__ void nw_finish_kernel(const int2* brow_last, const int2* rcol, const int2* halo, int ncols, int n2,
+                                 int jstart, int32_t* last_row, int32_t* last_col, int32_t* score, int* ack_out,
+                                 int epoch)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int jend = jstart + ncols;
+    for (int j = tid; j <= ncols; j += nth) {
+        int g = 0;                                           // G of the init row / init column
+        if (brow_last != nullptr) g = brow_last[j].y;
+        else if (n2 > 0 && halo != nullptr) g = halo[n2].y;  // ncols == 0, j == 0
+        last_row[j] = g - n2 - (jstart + j);
+    }
+    for (int i = tid; i <= n2; i += nth) {
+        int g = 0;
+        if (i > 0) {
+            if (rcol != nullptr) g = rcol[i].y;
+            else if (halo != nullptr) g = halo[i].y;
+        }
+        last_col[i] = g - i - jend;
+    }
+    if (tid == 0) {
+        int g = 0;
+        if (n2 > 0) {
+            if (rcol != nullptr) g = rcol[n2].y;
+            else if (halo != nullptr) g = halo[n2].y;
+        }
+        *score = g - n2 - jend;
+    }
+    // the halo mailbox of this epoch has been consumed: let the producer (which polls this word, over NVLink when it
+    // sits on another GPU) reuse it.  Stream order puts this kernel after the strip kernel.
+    if (ack_out != nullptr && tid == 0)
+        asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(ack_out), "r"(epoch) : "memory");
+}
+
+// strip boundary row k in H form (checkpoint rows kept in HBM)
+__global__ void nw_strip_row_kernel(const int2* brow, int ncols, int row_i, int jstart, int32_t* out)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int j = tid; j <= ncols; j += nth) out[j] = brow[j].y - row_i - (jstart + j);
+}
+
+// table column 0 of a part that has no interior column (n1 == 0): H[i][0] = -i (src/serial/serial.cpp:17)
+__global__ void nw_table_col0_kernel(int32_t* table, long long tpitch, int n2)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int i = tid + 1; i <= n2; i += nth) table[(long long)i * tpitch] = -i;
+}
+
+// presence bitmap over a large byte array (batch inputs), 16 bytes per load where aligned
+__global__ void nw_presence_kernel64(const uint8_t* s, long long n, uint32_t* bitmap /*8 words*/)
+{
+    __shared__ uint32_t bm[8];
+    if (threadIdx.x < 8) bm[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = gridDim.x * (long long)blockDim.x;
+    const long long head = min(n, (long long)((16 - ((uintptr_t)s & 15)) & 15));
+    for (long long i = tid; i < head; i += nth) loc[s[i] >> 5] |= 1u << (s[i] & 31);
+    const uint4* v = (const uint4*)(s + head);
+    const long long nv = (n - head) >> 4;
+    for (long long i = tid; i < nv; i += nth) {
+        const uint4 q = v[i];
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t x = (w[k] >> (8 * b)) & 0xffu;
+                loc[x >> 5] |= 1u << (x & 31);
+            }
+    }
+    for (long long i = head + (nv << 4) + tid; i < n; i += nth) loc[s[i] >> 5] |= 1u << (s[i] & 31);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (loc[k]) atomicOr(&bm[k], loc[k]);
+    __syncthreads();
+    if (threadIdx.x < 8 && bm[threadIdx.x]) atomicOr(&bitmap[threadIdx.x], bm[threadIdx.x]);
+}
+
+// integer / DPX pipe rate: 8 independent VIADDMNMX chains per thread (roofline denominator)
+constexpr int DPX_PEAK_OPS_PER_ITER = 8;
+__global__ void nw_dpx_peak_kernel(int* out, unsigned long long* clk, int iters, int seed)
+{
+    int x[8], a[8], c[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        x[k] = threadIdx.x + k + seed;
+        a[k] = (seed & 1) + k - 3;
+        c[k] = -(int)threadIdx.x - k;
+    }
+    unsigned long long t0 = 0, g0 = 0;
+    if (threadIdx.x == 0) {
+        t0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+    }
+#pragma unroll 4
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = __viaddmax_s32(x[k], a[k], c[k]);
+    }
+    int acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc ^= x[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) {
+        unsigned long long t1 = clock64(), g1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+        clk[2 * blockIdx.x] = t1 - t0;
+        clk[2 * blockIdx.x + 1] = g1 - g0;
+    }
+}
+
+}  // namespace nw
