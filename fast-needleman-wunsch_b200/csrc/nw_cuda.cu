@@ -117,7 +117,7 @@ struct nw_plan {
     bool generic = false, uploaded = false;
     int epoch = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     // device memory
     uint8_t *d_s1 = nullptr, *d_s2 = nullptr;
     uint32_t *d_wq = nullptr, *d_rsel = nullptr, *d_bitmap = nullptr;
@@ -229,6 +229,8 @@ extern "C" int nw_plan_destroy(nw_plan* p)
         if (b) cudaFree(b);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->ev2) cudaEventDestroy(p->ev2);
+    if (p->ev3) cudaEventDestroy(p->ev3);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
     return NW_OK;
@@ -241,6 +243,8 @@ static int plan_alloc(nw_plan* p, const nw_tuning* tuning)
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&p->ev0));
     CK(cudaEventCreate(&p->ev1));
+    CK(cudaEventCreate(&p->ev2));
+    CK(cudaEventCreate(&p->ev3));
 
     int R = tuning ? tuning->rows_per_lane : 0;
     if (R == 0) R = env_int("NW_CUDA_R", 0);
@@ -540,6 +544,24 @@ extern "C" int nw_plan_time(nw_plan* p, int iters, float* ms_per_fill)
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
     *ms_per_fill = ms / iters;
+    return NW_OK;
+}
+
+extern "C" int nw_plan_timer_start(nw_plan* p)
+{
+    if (!p) return fail(NW_ERR_ARG, "plan is NULL");
+    CK(cudaSetDevice(p->device));
+    CK(cudaEventRecord(p->ev2, p->stream));
+    return NW_OK;
+}
+
+extern "C" int nw_plan_timer_stop(nw_plan* p, float* ms)
+{
+    if (!p || !ms) return fail(NW_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(p->device));
+    CK(cudaEventRecord(p->ev3, p->stream));
+    CK(cudaEventSynchronize(p->ev3));
+    CK(cudaEventElapsedTime(ms, p->ev2, p->ev3));
     return NW_OK;
 }
 

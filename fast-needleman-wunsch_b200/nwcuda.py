@@ -20,7 +20,7 @@ EXPORTS = [
     "nw_cuda_fill", "nw_cuda_fill_ex", "nw_cuda_score", "nw_cuda_boundaries", "nw_cuda_batch_scores",
     "nw_plan_create", "nw_plan_destroy", "nw_plan_upload", "nw_plan_upload_device", "nw_plan_connect",
     "nw_plan_export_mailbox", "nw_plan_import_mailbox", "nw_plan_run", "nw_plan_sync", "nw_plan_time",
-    "nw_plan_last_ms", "nw_plan_launches_per_run", "nw_plan_score", "nw_plan_last_row", "nw_plan_last_col",
+    "nw_plan_timer_start", "nw_plan_timer_stop", "nw_plan_last_ms", "nw_plan_launches_per_run", "nw_plan_score", "nw_plan_last_row", "nw_plan_last_col",
     "nw_plan_table_to_host", "nw_plan_table_device", "nw_plan_strip_info", "nw_plan_strip_row",
     "nw_batch_create", "nw_batch_destroy", "nw_batch_upload", "nw_batch_upload_device", "nw_batch_run",
     "nw_batch_sync", "nw_batch_time", "nw_batch_scores", "nw_cuda_dpx_peak",
@@ -61,6 +61,7 @@ def lib():
             "nw_plan_connect": [vp, vp], "nw_plan_export_mailbox": [vp, vp],
             "nw_plan_import_mailbox": [vp, vp, C.c_int],
             "nw_plan_run": [vp], "nw_plan_sync": [vp], "nw_plan_time": [vp, C.c_int, C.POINTER(C.c_float)],
+            "nw_plan_timer_start": [vp], "nw_plan_timer_stop": [vp, C.POINTER(C.c_float)],
             "nw_plan_last_ms": [vp, C.POINTER(C.c_float)], "nw_plan_launches_per_run": [vp, ip],
             "nw_plan_score": [vp, vp], "nw_plan_last_row": [vp, vp], "nw_plan_last_col": [vp, vp],
             "nw_plan_table_to_host": [vp, vp], "nw_plan_table_device": [vp, C.POINTER(vp), C.POINTER(i64)],
@@ -231,6 +232,14 @@ class Plan:
     def time(self, iters=1):
         ms = C.c_float()
         _ck(lib().nw_plan_time(self._h, iters, C.byref(ms)))
+        return ms.value
+
+    def timer_start(self):
+        _ck(lib().nw_plan_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        _ck(lib().nw_plan_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
     def last_ms(self):

@@ -117,6 +117,10 @@ int nw_plan_sync(nw_plan* p);
 /* Run the fill `iters` times back to back and return the mean device time of one fill in milliseconds,
  * measured with CUDA events on the plan's own stream (sequences already resident). */
 int nw_plan_time(nw_plan* p, int iters, float* ms_per_fill);
+/* CUDA events on the plan's own stream around whatever is enqueued between the two calls (used to time the parts of a
+ * multi-GPU pipeline: each rank brackets its K fills, the job time is the maximum over ranks).  _stop synchronises. */
+int nw_plan_timer_start(nw_plan* p);
+int nw_plan_timer_stop(nw_plan* p, float* ms);
 /* Device time of the most recent nw_plan_run, CUDA events around the kernels only. */
 int nw_plan_last_ms(nw_plan* p, float* ms);
 /* Number of kernels one nw_plan_run launches. */
