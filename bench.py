@@ -259,21 +259,16 @@ def gpu_arm(args):
     cells = n1 * n2
 
     # every rank owns one column strip (part = rank); all parts must share the strip height chosen by rank 0
+    pipeline = importlib.import_module("fast-needleman-wunsch_b200.pipeline")
     R = args.rows_per_lane
-    if world > 1:
-        if R == 0:
-            probe = nw.Plan(n1, n2, mode=mode, device=device, part=0, nparts=world) if rank == 0 else None
-            box = [probe.strip_info()["rows_per_lane"] if rank == 0 else 0]
-            dist.broadcast_object_list(box, src=0)
-            R = box[0]
-            if probe is not None:
-                probe.close()
+    if world > 1 and R == 0:
+        def choose():
+            with nw.Plan(n1, n2, mode=mode, device=device, part=0, nparts=world) as probe:
+                return probe.strip_info()["rows_per_lane"]
+        R = pipeline.agree_rows_per_lane(dist, rank, choose)
     plan = nw.Plan(n1, n2, mode=mode, device=device, part=rank, nparts=world, rows_per_lane=R)
     if world > 1:
-        handles = [None] * world
-        dist.all_gather_object(handles, plan.export_mailbox() if rank > 0 else b"")
-        if rank + 1 < world:
-            plan.import_mailbox(handles[rank + 1], rank + 1)
+        pipeline.exchange_mailboxes(dist, plan, rank, world)
     plan.upload(s1, s2)
     plan.sync()
     info = plan.strip_info()

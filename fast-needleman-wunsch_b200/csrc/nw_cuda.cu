@@ -8,6 +8,7 @@
 #include "../../include/nw_cuda.h"
 #include "nw_kernels.cuh"
 #include "nw_batch.cuh"
+#include "nw_packed.cuh"
 
 #include <cooperative_groups.h>
 #include <algorithm>
@@ -73,6 +74,17 @@ StripKernel strip_kernel(int R, bool generic, bool full)
     }
 }
 
+StripKernel strip16_kernel(int regs)
+{
+    switch (regs) {
+    case 1: return nw::nw_strip16_kernel<1>;
+    case 2: return nw::nw_strip16_kernel<2>;
+    case 4: return nw::nw_strip16_kernel<4>;
+    case 8: return nw::nw_strip16_kernel<8>;
+    default: return nullptr;
+    }
+}
+
 typedef void (*BatchKernel)(const nw::BatchParams);
 BatchKernel batch_kernel(int R, bool generic)
 {
@@ -113,8 +125,12 @@ struct nw_plan {
     int n1 = 0, n2 = 0, mode = 0, part = 0, nparts = 1;
     int jstart = 0;       // global table column of this part's left boundary column
     int ncols = 0;        // interior columns of this part
-    int R = 4, warps = 8, ctas = 0, nstrips = 0, pad_top = 0;
+    int R = 4;            // table rows per lane: 1, 2, 4, 8 (32-bit kernels) or 2, 4, 8, 16 (packed kernel)
+    int R_req = 0, warps_req = 0, ctas_req = 0;      // what the caller asked for (0 = automatic)
+    int warps = 8, ctas = 0, nstrips = 0, pad_top = 0;
+    bool packed = false;  // nw_packed.cuh kernel (boundary mode, at most four distinct byte values)
     bool generic = false, uploaded = false;
+    size_t rsel_words = 0, brow_words = 0;
     int epoch = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
@@ -217,6 +233,27 @@ static int choose_rows_per_lane(int n2, int ncols, int sm_count)
     return bestR;
 }
 
+static int choose_rows_per_lane_packed(int n2, int ncols, int sm_count)
+{
+    // packed kernel: rows per lane = 2 * registers.  One warp per scheduler is enough; a strip lags its predecessor
+    // by ~64 columns of skew plus the hand-off latency.
+    const int cand[4] = {16, 8, 4, 2};
+    double best = 1e300;
+    int bestR = 8;
+    const double slots = sm_count * 4.0;
+    for (int ci = 0; ci < 4; ++ci) {
+        const int R = cand[ci];
+        const double strips = (n2 + 32.0 * R - 1) / (32.0 * R);
+        const double issue = 2.0 * (1.5 * R + 5.0);                       // cycles per step, one warp
+        const double chain = 27.0 + 2.0 * (R / 2) ;                       // shuffle + PRMT + max chain
+        const double rounds = std::max(1.0, strips / slots);
+        const double conc = std::min(strips, slots);
+        const double t = (ncols * rounds + conc * 110.0) * std::max(issue, chain);
+        if (t < best) { best = t; bestR = R; }
+    }
+    return bestR;
+}
+
 extern "C" int nw_plan_destroy(nw_plan* p)
 {
     if (!p) return NW_OK;
@@ -238,7 +275,6 @@ extern "C" int nw_plan_destroy(nw_plan* p)
 
 static int plan_alloc(nw_plan* p, const nw_tuning* tuning)
 {
-    const DeviceState& d = g_dev[p->device];
     CK(cudaSetDevice(p->device));
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&p->ev0));
@@ -246,28 +282,22 @@ static int plan_alloc(nw_plan* p, const nw_tuning* tuning)
     CK(cudaEventCreate(&p->ev2));
     CK(cudaEventCreate(&p->ev3));
 
-    int R = tuning ? tuning->rows_per_lane : 0;
-    if (R == 0) R = env_int("NW_CUDA_R", 0);
-    if (R == 0) R = choose_rows_per_lane(p->n2, p->ncols, d.sm_count);
-    if (R != 1 && R != 2 && R != 4 && R != 8) return fail(NW_ERR_ARG, "rows_per_lane must be 1, 2, 4 or 8 (got %d)", R);
-    p->R = R;
-    int warps = tuning ? tuning->warps_per_cta : 0;
-    if (warps == 0) warps = env_int("NW_CUDA_WARPS", 0);
-    if (warps == 0) warps = 8;
-    if (warps < 1 || warps > 16) return fail(NW_ERR_ARG, "warps_per_cta must be in 1..16 (got %d)", warps);
-    p->warps = warps;
-    p->nstrips = (int)(((long long)p->n2 + 32LL * R - 1) / (32LL * R));
-    p->pad_top = p->nstrips * 32 * R - p->n2;
+    p->R_req = tuning ? tuning->rows_per_lane : 0;
+    if (p->R_req == 0) p->R_req = env_int("NW_CUDA_R", 0);
+    p->warps_req = tuning ? tuning->warps_per_cta : 0;
+    if (p->warps_req == 0) p->warps_req = env_int("NW_CUDA_WARPS", 0);
+    p->ctas_req = tuning ? tuning->ctas : 0;
+    if (p->ctas_req == 0) p->ctas_req = env_int("NW_CUDA_CTAS", 0);
+    if (p->R_req != 0 && p->R_req != 1 && p->R_req != 2 && p->R_req != 4 && p->R_req != 8 && p->R_req != 16)
+        return fail(NW_ERR_ARG, "rows_per_lane must be 0 (auto), 1, 2, 4, 8 or 16 (got %d)", p->R_req);
+    if (p->warps_req < 0 || p->warps_req > 16) return fail(NW_ERR_ARG, "warps_per_cta must be in 0..16 (got %d)", p->warps_req);
 
     const int nc = p->ncols, n2 = p->n2;
     CK(cudaMalloc(&p->d_s1, (size_t)std::max(nc, 1)));
     CK(cudaMalloc(&p->d_s2, (size_t)std::max(n2, 1)));
     CK(cudaMalloc(&p->d_wq, sizeof(uint32_t) * ((size_t)nc + 2 * nw::WQ_PAD)));
-    CK(cudaMalloc(&p->d_rsel, sizeof(uint32_t) * (size_t)std::max(p->nstrips * 32 * R, 1)));
     CK(cudaMalloc(&p->d_bitmap, 8 * sizeof(uint32_t)));
     p->pitch = ((long long)nc + 1 + 15) & ~15LL;
-    CK(cudaMalloc(&p->d_brow, sizeof(int2) * (size_t)p->pitch * (size_t)std::max(p->nstrips, 1)));
-    CK(cudaMemset(p->d_brow, 0, sizeof(int2) * (size_t)p->pitch * (size_t)std::max(p->nstrips, 1)));
     p->mpitch = ((long long)n2 + 1 + 15) & ~15LL;
     if (p->part > 0) {
         CK(cudaMalloc(&p->d_mailbox, sizeof(int2) * 2 * (size_t)p->mpitch + 64));
@@ -285,25 +315,56 @@ static int plan_alloc(nw_plan* p, const nw_tuning* tuning)
     CK(cudaMalloc(&p->d_last_col, sizeof(int32_t) * ((size_t)n2 + 1)));
     CK(cudaMalloc(&p->d_tmp_row, sizeof(int32_t) * ((size_t)nc + 1)));
     CK(cudaMalloc(&p->d_score, 64));
-    p->smem = sizeof(uint32_t) * nw::SMEM_WORDS_PER_WARP * (size_t)p->warps;
     return NW_OK;
 }
 
-static int plan_pick_kernel(nw_plan* p, const nw_tuning* tuning)
+// Strip geometry and kernel choice; needs the alphabet, so it runs at upload time.  (Re)allocates what depends on it.
+static int plan_pick_kernel(nw_plan* p)
 {
     const DeviceState& d = g_dev[p->device];
-    p->kernel = strip_kernel(p->R, p->generic, p->mode == NW_MODE_FULL);
-    if (!p->kernel) return fail(NW_ERR_ARG, "no kernel for R=%d", p->R);
+    CK(cudaSetDevice(p->device));
+    p->packed = !p->generic && p->mode == NW_MODE_BOUNDARY && !env_int("NW_CUDA_NO_PACKED", 0) && p->R_req != 1;
+    int R = p->R_req;
+    if (R == 0) R = p->packed ? choose_rows_per_lane_packed(p->n2, p->ncols, d.sm_count)
+                              : choose_rows_per_lane(p->n2, p->ncols, d.sm_count);
+    if (!p->packed && R > 8) R = 8;
+    p->R = R;
+    p->warps = p->warps_req ? p->warps_req : (p->packed ? 4 : 8);
+    p->nstrips = (int)(((long long)p->n2 + 32LL * R - 1) / (32LL * R));
+    p->pad_top = p->nstrips * 32 * R - p->n2;
+    const size_t rsel_words = (size_t)std::max(p->nstrips * 32 * R, 1);
+    const size_t brow_words = (size_t)p->pitch * (size_t)std::max(p->nstrips, 1);
+    if (rsel_words > p->rsel_words) {
+        if (p->d_rsel) CK(cudaFree(p->d_rsel));
+        p->d_rsel = nullptr;
+        CK(cudaMalloc(&p->d_rsel, sizeof(uint32_t) * rsel_words));
+        p->rsel_words = rsel_words;
+    }
+    if (brow_words > p->brow_words) {
+        if (p->d_brow) CK(cudaFree(p->d_brow));
+        p->d_brow = nullptr;
+        CK(cudaMalloc(&p->d_brow, sizeof(int2) * brow_words));
+        CK(cudaMemsetAsync(p->d_brow, 0, sizeof(int2) * brow_words, p->stream));    // tags must not match any epoch
+        p->brow_words = brow_words;
+    }
+    if (p->packed) {
+        p->kernel = strip16_kernel(R / 2);
+        p->smem = sizeof(uint32_t) * nw::SMEM16_WORDS_PER_WARP * (size_t)p->warps;
+    } else {
+        p->kernel = strip_kernel(R, p->generic, p->mode == NW_MODE_FULL);
+        p->smem = sizeof(uint32_t) * nw::SMEM_WORDS_PER_WARP * (size_t)p->warps;
+    }
+    if (!p->kernel) return fail(NW_ERR_ARG, "no kernel for rows_per_lane=%d (%s)", R, p->packed ? "packed" : "32-bit");
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p->kernel, p->warps * 32, p->smem));
     if (per_sm < 1) return fail(NW_ERR_CUDA, "strip kernel does not fit on an SM (warps=%d)", p->warps);
-    // ~8 resident warps per SM by default (2 per scheduler): enough to cover shuffle and L2 latency
-    int target_warps_per_sm = env_int("NW_CUDA_WARPS_PER_SM", 8);
+    // 32-bit kernels: ~8 resident warps per SM (2 per scheduler) to cover shuffle latency; the packed kernel is
+    // issue-bound with one warp per scheduler
+    int target_warps_per_sm = env_int("NW_CUDA_WARPS_PER_SM", p->packed ? 4 : 8);
     int ctas_per_sm = std::max(1, std::min(per_sm, target_warps_per_sm / p->warps));
     int cap = d.sm_count * ctas_per_sm;
     int want = (p->nstrips + p->warps - 1) / p->warps;
-    int ctas = tuning ? tuning->ctas : 0;
-    if (ctas == 0) ctas = env_int("NW_CUDA_CTAS", 0);
+    int ctas = p->ctas_req;
     if (ctas == 0) ctas = std::min(cap, want);
     ctas = std::max(1, std::min(ctas, d.sm_count * per_sm));    // never more than can be co-resident
     p->ctas = ctas;
@@ -332,8 +393,8 @@ extern "C" int nw_plan_create(nw_plan** out, int device, int32_t n1, int32_t n2,
     p->nparts = nparts;
     partition(n1, nparts, part, &p->jstart, &p->ncols);
     rc = plan_alloc(p, tuning);
-    if (rc == NW_OK) rc = plan_pick_kernel(p, tuning);
-    if (rc != NW_OK) {
+    if (rc == NW_OK) rc = plan_pick_kernel(p);        // provisional (assumes the four-letter alphabet) so that
+    if (rc != NW_OK) {                                // nw_plan_strip_info answers before the first upload
         nw_plan_destroy(p);
         return rc;
     }
@@ -346,6 +407,8 @@ static int plan_encode(nw_plan* p, const bool seen[256])
     nw::EncodeParams e;
     p->generic = !build_code(seen, e.code);
     if (env_int("NW_CUDA_GENERIC", 0)) p->generic = true;
+    int rc = plan_pick_kernel(p);
+    if (rc) return rc;
     e.s1 = p->d_s1;
     e.s2 = p->d_s2;
     e.wq_base = p->d_wq;
@@ -355,10 +418,9 @@ static int plan_encode(nw_plan* p, const bool seen[256])
     e.nrows_padded = p->nstrips * 32 * p->R;
     e.pad_top = p->pad_top;
     e.generic = p->generic ? 1 : 0;
+    e.packed_regs = p->packed ? p->R / 2 : 0;
     nw::nw_encode_kernel<<<64, 256, 0, p->stream>>>(e);
     CK(cudaGetLastError());
-    int rc = plan_pick_kernel(p, nullptr);
-    if (rc) return rc;
     p->uploaded = true;
     return NW_OK;
 }
@@ -405,7 +467,6 @@ extern "C" int nw_plan_connect(nw_plan* left, nw_plan* right)
     if (!left || !right) return fail(NW_ERR_ARG, "plan is NULL");
     if (left->nparts != right->nparts || right->part != left->part + 1 || left->n1 != right->n1 || left->n2 != right->n2)
         return fail(NW_ERR_ARG, "plans are not adjacent parts of the same pipeline");
-    if (left->R != right->R) return fail(NW_ERR_ARG, "adjacent parts must use the same rows_per_lane");
     if (left->device != right->device) {
         int can = 0;
         CK(cudaDeviceCanAccessPeer(&can, left->device, right->device));

@@ -277,6 +277,7 @@ struct EncodeParams {
     uint32_t* rsel;         // nrows_padded words
     int ncols, n2, nrows_padded, pad_top;
     int generic;
+    int packed_regs;        // 0: 32-bit kernels; R > 0: packed kernel with R registers per lane (strip = 64*R rows)
     uint8_t code[256];      // 4-letter path: byte value -> 0..3
 };
 
@@ -289,6 +290,20 @@ __global__ void nw_encode_kernel(const EncodeParams e)
         if (c >= 0 && c < e.ncols) v = e.generic ? (uint32_t)e.s1[c] : 0x02020202u + (1u << (8 * e.code[e.s1[c]]));
         else v = e.generic ? 0x100u : 0x02020202u;
         e.wq_base[x] = v;
+    }
+    if (e.packed_regs > 0) {
+        // packed kernel (nw_packed.cuh): one PRMT selector per (strip, lane, register): nibble 0 picks the low half's
+        // weight byte from the column word of column c, nibble 2 the high half's from the word of column c-32;
+        // nibbles 1 and 3 (and both of a virtual row) replicate the sign of a small positive byte, i.e. give zero
+        const int R = e.packed_regs;
+        for (int x = tid; x < e.nrows_padded / 2; x += nth) {
+            const int s = x / (32 * R), rem = x - s * 32 * R, L = rem / R, r = rem - L * R;
+            const int klo = s * 64 * R + L * R + r - e.pad_top, khi = klo + 32 * R;
+            const uint32_t n0 = (klo >= 0) ? e.code[e.s2[klo]] : 0x8u;
+            const uint32_t n2 = (khi >= 0) ? 4u + e.code[e.s2[khi]] : 0xCu;
+            e.rsel[x] = n0 | 0x80u | (n2 << 8) | 0xC000u;
+        }
+        return;
     }
     for (int q = tid; q < e.nrows_padded; q += nth) {
         const int k = q - e.pad_top;     // index into s2

@@ -1,0 +1,229 @@
+// nw_packed.cuh -- the boundary-mode strip sweep on packed 16-bit lanes (DPX s16x2): two table rows per register.
+//
+// Same recurrence, same G = H + i + j change of variable and the same strip / tagged-boundary-row scheme as
+// nw_kernels.cuh (reference arithmetic: src/serial/serial.cpp:12-31), but every 32-bit register carries TWO cells:
+//   * a warp is 64 "virtual lanes" of R rows each: lane L holds virtual lane L in the low halves and virtual lane
+//     L+32 in the high halves of h[0..R-1]; virtual lane v works on column t - v at step t, so the low half of lane L
+//     is at column c = t - L and the high half at column c - 32;
+//   * one rotating shuffle of the packed h[R-1] feeds both halves of the next lane (lane 0 takes its low half from the
+//     strip's top boundary row and its high half from lane 31's low half: one PRMT with a per-lane selector);
+//   * one PRMT builds both substitution weights from the two column profile words, then VIADDMNMX.S16x2 and
+//     VIMNMX(3).S16x2 update both cells: 3 integer-pipe instructions per TWO cells.
+// 16 bits are enough because cells that are live in a warp at the same time differ by at most 3 * (rows + columns of
+// the live window) < 2^12; the warp keeps a running int32 `base` (stored = G - base) and re-bases every 32 blocks.
+// Boundary rows / columns leave the kernel as absolute int32 G, exactly like the 32-bit kernel, so the two kernels
+// interoperate (column-strip pipelines, checkpoint rows, finish kernel).
+#pragma once
+#include "nw_kernels.cuh"
+
+namespace nw {
+
+constexpr int RING_COPY_WORDS = 136;                       // 128-column ring + 8 words of bank skew per copy
+constexpr int SMEM16_WORDS_PER_WARP = 4 * RING_COPY_WORDS + 32 + 32;   // 4 ring copies + top inputs + bottom outputs
+
+template <int R, bool PRED>
+__device__ __forceinline__ void sweep16(uint32_t (&h)[R], uint32_t& dprev, const uint32_t (&sel)[R],
+                                        const uint32_t upsel, const int src_lane, const uint32_t* __restrict__ ringm,
+                                        const uint32_t* __restrict__ sin, uint32_t* sout, const int lane, const int cb,
+                                        const int ncols)
+{
+    const int i0 = cb - lane + (lane & 3);      // ring index (before & 127) of this lane's low column at k = 0; 4 | i0
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+        const uint4 clo = *reinterpret_cast<const uint4*>(ringm + ((i0 + 4 * k4) & 127));
+        const uint4 chi = *reinterpret_cast<const uint4*>(ringm + ((i0 + 4 * k4 - 32) & 127));
+        const uint4 tin = *reinterpret_cast<const uint4*>(sin + 4 * k4);
+        const uint32_t cl[4] = {clo.x, clo.y, clo.z, clo.w};
+        const uint32_t ch[4] = {chi.x, chi.y, chi.z, chi.w};
+        const uint32_t tn[4] = {tin.x, tin.y, tin.z, tin.w};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const int k = 4 * k4 + kk;
+            const uint32_t s = __shfl_sync(FULL_MASK, h[R - 1], src_lane);
+            const uint32_t up0 = prmt(s, tn[kk], upsel);       // {low: row above at col c, high: row above at col c-32}
+            uint32_t t[R];
+            uint32_t diag = dprev;
+            dprev = up0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t w = prmt(cl[kk], ch[kk], sel[r]);
+                t[r] = __viaddmax_s16x2(diag, w, h[r]);         // max(G[i-1][j-1] + w, G[i][j-1]) for both halves
+                diag = h[r];
+            }
+            uint32_t mask = 0xffffffffu;
+            if (PRED) {
+                const int col = cb + k - lane;
+                mask = ((unsigned)col < (unsigned)ncols ? 0x0000ffffu : 0u) |
+                       ((unsigned)(col - 32) < (unsigned)ncols ? 0xffff0000u : 0u);
+            }
+            uint32_t g = up0;                                   // running max down the rows; every second link is a 3-max
+#pragma unroll
+            for (int r = 0; r < R; r += 2) {
+                const uint32_t ga = __vmaxs2(t[r], g);
+                uint32_t gb = ga;
+                if (r + 1 < R) gb = __vimax3_s16x2(t[r + 1], t[r], g);
+                if (PRED) {
+                    h[r] = (ga & mask) | (h[r] & ~mask);
+                    if (r + 1 < R) h[r + 1] = (gb & mask) | (h[r + 1] & ~mask);
+                } else {
+                    h[r] = ga;
+                    if (r + 1 < R) h[r + 1] = gb;
+                }
+                g = gb;
+            }
+            if (lane == 31) sout[k] = h[R - 1];
+        }
+    }
+}
+
+__device__ __forceinline__ int2 poll_tagged(const int2* p, int epoch, int sys)
+{
+    int2 t;
+    for (;;) {
+        t = sys ? ld_tagged_sys(p) : ld_tagged_gpu(p);
+        if (t.x == epoch) return t;
+        __nanosleep(200);
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void run_strip16(const StripParams& p, const int s, const int lane, uint32_t* smem)
+{
+    constexpr int SH = 64 * R;
+    uint32_t* ring = smem;
+    uint32_t* sin = smem + 4 * RING_COPY_WORDS;
+    uint32_t* sout = sin + 32;
+    const uint32_t* ringm = ring + (lane & 3) * RING_COPY_WORDS;
+    const int ncols = p.ncols;
+    const int q_lo = s * SH + lane * R;               // first padded row of the low half; the high half is 32*R below
+    const int i_lo = q_lo - p.pad_top;                // table row just above the low half's first row (may be <= 0)
+    const int i_hi = i_lo + 32 * R;
+
+    uint32_t sel[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) sel[r] = p.rsel[(s * 32 + lane) * R + r];
+    const uint32_t upsel = (lane == 0) ? 0x1054u : 0x3210u;
+    const int src_lane = (lane + 31) & 31;
+
+    // left boundary column.  Whole table: G = 0.  Column strip: the neighbour's right column (absolute G); the warp's
+    // base starts at its minimum so that the stored values are small.
+    int base = 0;
+    uint32_t h[R];
+    uint32_t dprev = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) h[r] = 0;
+    if (p.halo != nullptr) {
+        int lo[R + 1], hi[R + 1];
+        int mn = 0x7fffffff;
+#pragma unroll
+        for (int r = -1; r < R; ++r) {
+            const int a = i_lo + 1 + r, b = i_hi + 1 + r;
+            lo[r + 1] = (a >= 1) ? poll_tagged(p.halo + a, p.epoch, p.halo_sys).y : 0;
+            hi[r + 1] = (b >= 1) ? poll_tagged(p.halo + b, p.epoch, p.halo_sys).y : 0;
+            mn = min(mn, min(lo[r + 1], hi[r + 1]));
+        }
+        base = max(__reduce_min_sync(FULL_MASK, mn) - 8, 0);
+        dprev = ((uint32_t)(lo[0] - base) & 0xffffu) | ((uint32_t)(hi[0] - base) << 16);
+#pragma unroll
+        for (int r = 0; r < R; ++r) h[r] = ((uint32_t)(lo[r + 1] - base) & 0xffffu) | ((uint32_t)(hi[r + 1] - base) << 16);
+    }
+
+    int2* tout = p.brow + (long long)s * p.pitch;
+    const int2* tin = p.brow + (long long)(s - 1) * p.pitch;
+    if (lane == 31) st_tagged_gpu(tout, p.epoch, ((int)h[R - 1] >> 16) + base);      // j = 0: the boundary column
+
+    const uint32_t* wq = p.wq;
+    uint32_t wnext = wq[lane];
+    int2 pre = make_int2(0, 0);
+    if (s > 0 && lane < ncols) pre = ld_tagged_gpu(tin + lane + 1);
+
+    const int nblocks = (ncols + 63 + 31) >> 5;          // the high half of lane 31 reaches column ncols-1 at t = ncols+62
+    for (int b = 0; b < nblocks; ++b) {
+        const int cb = b << 5;
+        // column operands of [cb, cb+32) into the four skewed ring copies; the ring then holds [cb-96, cb+32)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) ring[m * RING_COPY_WORDS + ((cb + lane + m) & 127)] = wnext;
+        {
+            const int nc = cb + 32 + lane;
+            wnext = wq[nc < ncols + WQ_PAD ? nc : ncols + WQ_PAD - 1];
+        }
+        // top boundary row of [cb, cb+32) -> stored form, low half
+        if (cb < ncols) {
+            int v = 0;
+            if (s > 0) {
+                const int col = cb + lane;
+                const bool need = col < ncols;
+                while (!__all_sync(FULL_MASK, !need || pre.x == p.epoch)) {
+                    if (need && pre.x != p.epoch) pre = ld_tagged_gpu(tin + col + 1);
+                }
+                v = pre.y;
+                if (col + 32 < ncols) pre = ld_tagged_gpu(tin + col + 33);
+            }
+            sin[lane] = (uint32_t)(v - base) & 0xffffu;
+        }
+        __syncwarp();
+        if (cb >= 64 && cb + 31 < ncols)
+            sweep16<R, false>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols);
+        else
+            sweep16<R, true>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols);
+        __syncwarp();
+        {
+            const int oc = cb - 63 + lane;               // column finished by the high half of lane 31 at step k = lane
+            if (oc >= 0 && oc < ncols) st_tagged_gpu(tout + oc + 1, p.epoch, ((int)sout[lane] >> 16) + base);
+        }
+        if ((b & 31) == 31) {                            // re-base: keep the stored values small
+            uint32_t mm = dprev;
+#pragma unroll
+            for (int r = 0; r < R; ++r) mm = __vmins2(mm, h[r]);
+            int m = min((int)(short)(mm & 0xffffu), (int)mm >> 16);
+            m = __reduce_min_sync(FULL_MASK, m);
+            const int D = m - 8;
+            if (D > 0) {
+                const uint32_t Dp = (uint32_t)D * 0x10001u;       // every half is >= D: no borrow between halves
+#pragma unroll
+                for (int r = 0; r < R; ++r) h[r] -= Dp;
+                dprev -= Dp;
+                base += D;
+            }
+        }
+    }
+
+    // right boundary column of this lane's rows (absolute G)
+    if (p.rcol != nullptr) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int a = i_lo + 1 + r, b = i_hi + 1 + r;
+            const int va = (int)(short)(h[r] & 0xffffu) + base, vb = ((int)h[r] >> 16) + base;
+            if (p.rcol_sys) {
+                if (a >= 1) st_tagged_sys(p.rcol + a, p.epoch, va);
+                if (b >= 1) st_tagged_sys(p.rcol + b, p.epoch, vb);
+            } else {
+                if (a >= 1) st_tagged_gpu(p.rcol + a, p.epoch, va);
+                if (b >= 1) st_tagged_gpu(p.rcol + b, p.epoch, vb);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <int R>
+__global__ void __launch_bounds__(512) nw_strip16_kernel(const StripParams p)
+{
+    extern __shared__ __align__(16) uint32_t nw_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint32_t* smem = nw_smem + warp * SMEM16_WORDS_PER_WARP;
+    const int slot = blockIdx.x * nwarps + warp, nslots = gridDim.x * nwarps;
+    if (p.ack_in != nullptr) {          // do not overwrite a mailbox the consumer has not finished reading
+        if (threadIdx.x == 0) {
+            int a;
+            do {
+                asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(a) : "l"(p.ack_in) : "memory");
+                if (a < p.epoch - 2) __nanosleep(500);
+            } while (a < p.epoch - 2);
+        }
+        __syncthreads();
+    }
+    for (int s = slot; s < p.nstrips; s += nslots) run_strip16<R>(p, s, lane, smem);
+}
+
+}  // namespace nw

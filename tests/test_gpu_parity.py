@@ -63,15 +63,25 @@ def test_boundary_mode_writes_only_the_score(gpu):
 
 
 @pytest.mark.parametrize("name", ["smid", "2gb"])
-def test_boundaries_match_golden_hashes(gpu, oracle, name):
+def test_boundaries_match_golden_hashes(gpu, oracle, name, kernel_kind):
     s1, s2 = load_pair(name)
     row, col, sc = gpu.boundaries(s1, s2)
     g = GOLDEN["tables"][name]
     assert oracle.fnv(row) == g["fnv_lastrow"] and oracle.fnv(col) == g["fnv_lastcol"] and sc == g["score"]
 
 
-@pytest.mark.parametrize("R", [1, 2, 4, 8])
-def test_checkpoint_rows(gpu, oracle, R):
+@pytest.fixture(params=["packed16", "int32"])
+def kernel_kind(request, monkeypatch):
+    """Boundary mode has two kernels: packed s16x2 (nw_packed.cuh, default) and 32-bit (nw_kernels.cuh)."""
+    if request.param == "int32":
+        monkeypatch.setenv("NW_CUDA_NO_PACKED", "1")
+    return request.param
+
+
+@pytest.mark.parametrize("R", [1, 2, 4, 8, 16])
+def test_checkpoint_rows(gpu, oracle, R, kernel_kind):
+    if R == 16 and kernel_kind == "int32":
+        pytest.skip("16 rows per lane exists only in the packed kernel")
     s1, s2 = synth_pair(31, 1500, 2000, 5)
     with gpu.Plan(s1.size, s2.size, rows_per_lane=R) as p:
         p.upload(s1, s2)
@@ -86,7 +96,7 @@ def test_checkpoint_rows(gpu, oracle, R):
 
 @pytest.mark.parametrize("shape", [(0, 0), (0, 5), (5, 0), (1, 1), (1, 40), (40, 1), (31, 33), (33, 31), (64, 64),
                                    (65, 255), (255, 65), (2, 3000), (3000, 2), (777, 1025)])
-def test_edge_shapes(gpu, oracle, shape):
+def test_edge_shapes(gpu, oracle, shape, kernel_kind):
     n1, n2 = shape
     s1, s2 = synth_pair(100 + n1 + 7 * n2, n1, n2, 5)
     t = oracle.fill(s1, s2)
@@ -95,14 +105,36 @@ def test_edge_shapes(gpu, oracle, shape):
     assert np.array_equal(row, t[-1]) and np.array_equal(col, t[:, -1]) and sc == t[-1, -1]
 
 
-def test_many_random_shapes(gpu, oracle):
+def test_many_random_shapes(gpu, oracle, kernel_kind):
     rng = np.random.default_rng(5)
     for _ in range(40):
         n1, n2 = int(rng.integers(1, 700)), int(rng.integers(1, 700))
         hi = int(rng.choice([2, 3, 5, 9, 120]))
         s1 = rng.integers(1, hi, size=n1, dtype=np.int8)
         s2 = rng.integers(1, hi, size=n2, dtype=np.int8)
-        assert np.array_equal(gpu.needlemanWunsch(s1, s2), oracle.fill(s1, s2)), (n1, n2, hi)
+        t = oracle.fill(s1, s2)
+        assert np.array_equal(gpu.needlemanWunsch(s1, s2), t), (n1, n2, hi)
+        row, col, sc = gpu.boundaries(s1, s2)
+        assert np.array_equal(row, t[-1]) and np.array_equal(col, t[:, -1]) and sc == t[-1, -1], (n1, n2, hi)
+
+
+@pytest.mark.parametrize("R", [0, 2, 4, 8, 16])
+def test_boundaries_long_rows_rebase(gpu, oracle, R):
+    # wide tables make the packed kernel re-base its 16-bit lanes many times; identical prefixes make G grow fastest
+    rng = np.random.default_rng(9)
+    s1 = rng.integers(1, 5, size=40000, dtype=np.int8)
+    s2 = np.concatenate([s1[:1500], rng.integers(1, 5, size=700, dtype=np.int8)]).astype(np.int8)
+    with gpu.Plan(s1.size, s2.size, rows_per_lane=R) as p:
+        p.upload(s1, s2)
+        p.run()
+        row, col, _, _ = oracle.boundaries(s1, s2)
+        assert np.array_equal(p.last_row(), row) and np.array_equal(p.last_col(), col)
+    # tall and narrow: many strips, few columns
+    with gpu.Plan(s2.size, s1.size, rows_per_lane=R) as p:
+        p.upload(s2, s1)
+        p.run()
+        row, col, _, _ = oracle.boundaries(s2, s1)
+        assert np.array_equal(p.last_row(), row) and np.array_equal(p.last_col(), col)
 
 
 def test_generic_alphabet_and_negative_bytes(gpu, oracle):
@@ -134,7 +166,7 @@ def test_repeated_runs_and_reupload(gpu, oracle):
 # ---- column strips (mpi-vert decomposition) on ONE device, parts run one after the other -------------------------------
 @pytest.mark.parametrize("P", [2, 3, 8])
 @pytest.mark.parametrize("mode", ["boundary", "full"])
-def test_column_strips_sequential(gpu, oracle, P, mode):
+def test_column_strips_sequential(gpu, oracle, P, mode, kernel_kind):
     s1, s2 = synth_pair(51, 3003, 1700, 5)
     t = oracle.fill(s1, s2)
     m = gpu.NW_MODE_FULL if mode == "full" else gpu.NW_MODE_BOUNDARY
