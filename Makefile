@@ -5,10 +5,10 @@ NVCC   ?= /usr/local/cuda/bin/nvcc
 CXX    := /usr/bin/g++
 REF    ?= /root/reference
 ARCH   := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS:= $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
+NVFLAGS:= $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $(EXTRA)
 LIB    := $(PKG)/libnw_cuda.so
 SRCS   := $(PKG)/csrc/nw_cuda.cu
-HDRS   := $(PKG)/csrc/nw_kernels.cuh $(PKG)/csrc/nw_batch.cuh include/nw_cuda.h
+HDRS   := $(wildcard $(PKG)/csrc/*.cuh) include/nw_cuda.h
 
 .PHONY: all lib driver oracle clean
 all: lib oracle driver

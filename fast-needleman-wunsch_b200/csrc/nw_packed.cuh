@@ -21,6 +21,10 @@ namespace nw {
 constexpr int RING_COPY_WORDS = 136;                       // 128-column ring + 8 words of bank skew per copy
 constexpr int SMEM16_WORDS_PER_WARP = 4 * RING_COPY_WORDS + 32 + 32;   // 4 ring copies + top inputs + bottom outputs
 
+// One 32-step block.  The per-step loop-carried chain is  SHFL -> PRMT -> max  (the running max down the rows is
+// computed as  G[r] = max(P[r], up)  with the prefix maxima P[r] of the t[] off the chain): with one warp per scheduler
+// the kernel is bound by that latency, not by issue slots, so the R-1 extra max instructions are free.  The operand
+// vectors of the next 4 steps are loaded before the current 4 are computed (shared-memory latency off the chain too).
 template <int R, bool PRED>
 __device__ __forceinline__ void sweep16(uint32_t (&h)[R], uint32_t& dprev, const uint32_t (&sel)[R],
                                         const uint32_t upsel, const int src_lane, const uint32_t* __restrict__ ringm,
@@ -28,50 +32,61 @@ __device__ __forceinline__ void sweep16(uint32_t (&h)[R], uint32_t& dprev, const
                                         const int ncols)
 {
     const int i0 = cb - lane + (lane & 3);      // ring index (before & 127) of this lane's low column at k = 0; 4 | i0
+    uint4 clo = *reinterpret_cast<const uint4*>(ringm + (i0 & 127));
+    uint4 chi = *reinterpret_cast<const uint4*>(ringm + ((i0 - 32) & 127));
+    uint4 tin = *reinterpret_cast<const uint4*>(sin);
 #pragma unroll
     for (int k4 = 0; k4 < 8; ++k4) {
-        const uint4 clo = *reinterpret_cast<const uint4*>(ringm + ((i0 + 4 * k4) & 127));
-        const uint4 chi = *reinterpret_cast<const uint4*>(ringm + ((i0 + 4 * k4 - 32) & 127));
-        const uint4 tin = *reinterpret_cast<const uint4*>(sin + 4 * k4);
         const uint32_t cl[4] = {clo.x, clo.y, clo.z, clo.w};
         const uint32_t ch[4] = {chi.x, chi.y, chi.z, chi.w};
         const uint32_t tn[4] = {tin.x, tin.y, tin.z, tin.w};
+#ifndef NW_DBG_NO_LDS
+        if (k4 < 7) {
+            clo = *reinterpret_cast<const uint4*>(ringm + ((i0 + 4 * k4 + 4) & 127));
+            chi = *reinterpret_cast<const uint4*>(ringm + ((i0 + 4 * k4 + 4 - 32) & 127));
+            tin = *reinterpret_cast<const uint4*>(sin + 4 * k4 + 4);
+        }
+#endif
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             const int k = 4 * k4 + kk;
             const uint32_t s = __shfl_sync(FULL_MASK, h[R - 1], src_lane);
-            const uint32_t up0 = prmt(s, tn[kk], upsel);       // {low: row above at col c, high: row above at col c-32}
+            // off the chain: t[r] = max(G[i-1][j-1] + w, G[i][j-1]) and their prefix maxima, both halves at once
             uint32_t t[R];
-            uint32_t diag = dprev;
-            dprev = up0;
+            {
+                uint32_t diag = dprev;
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint32_t w = prmt(cl[kk], ch[kk], sel[r]);
-                t[r] = __viaddmax_s16x2(diag, w, h[r]);         // max(G[i-1][j-1] + w, G[i][j-1]) for both halves
-                diag = h[r];
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t w = prmt(cl[kk], ch[kk], sel[r]);
+                    t[r] = __viaddmax_s16x2(diag, w, h[r]);
+                    diag = h[r];
+                }
             }
+            // prefix maxima of t[0..r-1] (off the chain), then G[r] = max3(t[r], P[r-1], up): one instruction per row
+            uint32_t P[R];
+            P[0] = t[0];
+#pragma unroll
+            for (int r = 1; r + 1 < R; ++r) P[r] = __vmaxs2(t[r], P[r - 1]);
+            const uint32_t up0 = prmt(s, tn[kk], upsel);       // {low: row above at col c, high: row above at col c-32}
+            dprev = up0;
             uint32_t mask = 0xffffffffu;
             if (PRED) {
                 const int col = cb + k - lane;
                 mask = ((unsigned)col < (unsigned)ncols ? 0x0000ffffu : 0u) |
                        ((unsigned)(col - 32) < (unsigned)ncols ? 0xffff0000u : 0u);
             }
-            uint32_t g = up0;                                   // running max down the rows; every second link is a 3-max
-#pragma unroll
-            for (int r = 0; r < R; r += 2) {
-                const uint32_t ga = __vmaxs2(t[r], g);
-                uint32_t gb = ga;
-                if (r + 1 < R) gb = __vimax3_s16x2(t[r + 1], t[r], g);
-                if (PRED) {
-                    h[r] = (ga & mask) | (h[r] & ~mask);
-                    if (r + 1 < R) h[r + 1] = (gb & mask) | (h[r + 1] & ~mask);
-                } else {
-                    h[r] = ga;
-                    if (r + 1 < R) h[r + 1] = gb;
-                }
-                g = gb;
+            {   // the last row first: it feeds the next step's shuffle
+                const uint32_t g = (R > 1) ? __vimax3_s16x2(t[R - 1], P[R > 1 ? R - 2 : 0], up0) : __vmaxs2(t[0], up0);
+                h[R - 1] = PRED ? ((g & mask) | (h[R - 1] & ~mask)) : g;
             }
+#pragma unroll
+            for (int r = 0; r + 1 < R; ++r) {
+                const uint32_t g = (r == 0) ? __vmaxs2(t[0], up0) : __vimax3_s16x2(t[r], P[r - 1], up0);
+                h[r] = PRED ? ((g & mask) | (h[r] & ~mask)) : g;
+            }
+#ifndef NW_DBG_NO_STS
             if (lane == 31) sout[k] = h[R - 1];
+#endif
         }
     }
 }

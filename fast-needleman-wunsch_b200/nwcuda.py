@@ -13,7 +13,7 @@ NW_MODE_BOUNDARY = 0
 NW_MODE_FULL = 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-lib_path = os.path.join(_HERE, "libnw_cuda.so")
+lib_path = os.environ.get("NW_CUDA_LIB", os.path.join(_HERE, "libnw_cuda.so"))   # override: A/B builds in development
 
 EXPORTS = [
     "nw_cuda_version", "nw_cuda_last_error", "nw_cuda_device_count", "nw_cuda_init", "nw_cuda_device_info",

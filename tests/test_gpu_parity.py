@@ -256,3 +256,47 @@ def test_driver_binary_prints_reference_format(gpu):
     assert out.returncode == 1 and "incorrect number of arguments" in out.stdout
     out = subprocess.run([exe, a, "/nonexistent.bdna"], capture_output=True, text=True)
     assert out.returncode == 1 and "ERROR: no such file /nonexistent.bdna" in out.stdout
+
+
+# ---- more than one GPU (skipped on a 1-GPU box; run with gpurun --gpus 2) -------------------------------------------------
+def _need_gpus(gpu, n):
+    if gpu.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+
+
+@pytest.mark.parametrize("ngpus", [2, 4])
+def test_multi_gpu_in_process_pipeline(gpu, oracle, ngpus):
+    # nw_cuda_fill_ex with ngpus > 1: column strips on devices 0..n-1 of ONE process, boundary column stored straight
+    # into the right neighbour's mailbox over NVLink, all kernels in flight at once
+    _need_gpus(gpu, ngpus)
+    s1, s2 = synth_pair(61, 20011, 9000, 5)
+    t = oracle.fill(s1, s2)
+    got = gpu.needlemanWunsch(s1, s2, mode=gpu.NW_MODE_FULL, ngpus=ngpus)
+    assert np.array_equal(got, t)
+    tb = np.zeros_like(t)
+    gpu.needlemanWunsch(s1, s2, tb, mode=gpu.NW_MODE_BOUNDARY, ngpus=ngpus)
+    assert tb[-1, -1] == t[-1, -1]
+
+
+def test_multi_gpu_64gb_score(gpu):
+    _need_gpus(gpu, 2)
+    s1, s2 = load_pair("64gb")
+    n = gpu.device_count()
+    for g in sorted({2, min(n, 4), min(n, 8)}):
+        t = np.zeros(1, dtype=np.int32)   # boundary mode writes only the last cell: hand it a 1-cell view trick is not
+        # allowed (the ABI indexes (n1+1)*(n2+1)-1), so use the plan API instead
+        plans = [gpu.Plan(s1.size, s2.size, device=d, part=d, nparts=g, rows_per_lane=8) for d in range(g)]
+        try:
+            for a, b in zip(plans, plans[1:]):
+                a.connect(b)
+            for p in plans:
+                p.upload(s1, s2)
+            for rep in range(3):
+                for p in plans:
+                    p.run()
+            for p in plans:
+                p.sync()
+            assert plans[-1].score() == GOLDEN["fixtures"]["64gb"]["score"]
+        finally:
+            for p in plans:
+                p.close()

@@ -19,7 +19,7 @@ def run(n1, n2, R, warps=8, ctas=0, tag=""):
         return ms
 
 nw.init(0)
-for R in (2, 4, 8):
+for R in (4, 8, 16):
     run(1 << 20, 32 * R, R, warps=1, tag="1 warp alone       ")
     run(1 << 20, 32 * R * 4, R, warps=4, tag="4 warps, 1/SMSP    ")
     run(1 << 20, 32 * R * 8, R, warps=8, tag="8 warps, 2/SMSP    ")
