@@ -234,6 +234,15 @@ def measured_peaks():
         return {}
 
 
+def ncu_traffic(name, full):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of the same workload, else None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t[name + ("-full" if full else "")]["bytes"]
+    except Exception:
+        return None
+
+
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -377,7 +386,7 @@ def gpu_arm(args):
                 "hbm": {"achieved_gbs": hbm_bytes / (ms_step * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
                         "peak_source": "MEASURED_PEAKS.json" if peaks.get("hbm_gbs") else "absent",
                         "algorithmic_bytes_per_step": hbm_bytes},
-                "dependency_bound_steps": n1 + info["nstrips"] * 32, "traffic": None}
+                "dependency_bound_steps": n1 + info["nstrips"] * 32, "traffic": ncu_traffic(name, mode == nw.NW_MODE_FULL)}
         if mode == nw.NW_MODE_FULL and peaks.get("hbm_gbs"):
             roof.update({"achieved": hbm_bytes / (ms_step * 1e-3) / 1e9, "peak": peaks["hbm_gbs"] * world, "unit": "GB/s",
                          "frac": hbm_bytes / (ms_step * 1e-3) / 1e9 / (peaks["hbm_gbs"] * world)})

@@ -104,3 +104,82 @@ __global__ void __launch_bounds__(256) nw_batch_kernel(const BatchParams p)
 }
 
 }  // namespace nw
+
+// ---- packed (s16x2) batch kernel ----------------------------------------------------------------------------------------
+// One warp per pair, the 64-virtual-lane sweep of nw_packed.cuh (two cells per register), no re-basing: the host only
+// selects this kernel when 3 * min(len1, len2) + 64 fits 15 bits, so absolute G values fit the 16-bit lanes.
+// Rows beyond one strip (64*R rows) are handled strip after strip by the same warp through a per-warp scratch row.
+#include "nw_packed.cuh"
+
+namespace nw {
+
+template <int R>
+__global__ void __launch_bounds__(128) nw_batch16_kernel(const BatchParams p)
+{
+    extern __shared__ __align__(16) uint32_t nw_smem[];
+    __shared__ uint8_t lut[256];
+    for (int x = threadIdx.x; x < 256; x += blockDim.x) lut[x] = p.code[x];
+    __syncthreads();
+
+    constexpr int SH = 64 * R;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint32_t* ring = nw_smem + warp * SMEM16_WORDS_PER_WARP;
+    uint32_t* sin = ring + 4 * RING_COPY_WORDS;
+    uint32_t* sout = sin + 32;
+    const uint32_t* ringm = ring + (lane & 3) * RING_COPY_WORDS;
+    const long long gw = (long long)blockIdx.x * nwarps + warp, nw_total = (long long)gridDim.x * nwarps;
+    int32_t* scratch = p.scratch + gw * p.scratch_pitch;
+    const int ncols = p.len1;
+    const int nblocks = (ncols + 63 + 31) >> 5;
+    const uint32_t upsel = (lane == 0) ? 0x1054u : 0x3210u;
+    const int src_lane = (lane + 31) & 31;
+
+    for (long long pair = gw; pair < p.npairs; pair += nw_total) {
+        const uint8_t* s1 = p.S1 + pair * p.len1;
+        const uint8_t* s2 = p.S2 + pair * p.len2;
+        uint32_t h[R];
+        for (int s = 0; s < p.nstrips; ++s) {
+            uint32_t sel[R];
+            const int klo0 = s * SH + lane * R - p.pad_top, khi0 = klo0 + 32 * R;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int klo = klo0 + r, khi = khi0 + r;
+                const uint32_t n0 = (klo >= 0) ? lut[s2[klo]] : 0x8u;
+                const uint32_t n2 = (khi >= 0) ? 4u + lut[s2[khi]] : 0xCu;
+                sel[r] = n0 | 0x80u | (n2 << 8) | 0xC000u;
+            }
+            uint32_t dprev = 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) h[r] = 0;
+            uint32_t wnext = batch_col_operand<false>(s1, lane, ncols, lut);
+            int pre = 0;
+            if (s > 0 && lane < ncols) pre = scratch[lane];
+            for (int b = 0; b < nblocks; ++b) {
+                const int cb = b << 5;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) ring[m * RING_COPY_WORDS + ((cb + lane + m) & 127)] = wnext;
+                wnext = batch_col_operand<false>(s1, cb + 32 + lane, ncols, lut);
+                if (cb < ncols) {
+                    sin[lane] = (uint32_t)pre & 0xffffu;
+                    if (s > 0 && cb + 32 + lane < ncols) pre = scratch[cb + 32 + lane];
+                }
+                __syncwarp();
+                if (cb >= 64 && cb + 31 < ncols)
+                    sweep16<R, false>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols);
+                else
+                    sweep16<R, true>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols);
+                __syncwarp();
+                if (s + 1 < p.nstrips) {
+                    const int oc = cb - 63 + lane;
+                    if (oc >= 0 && oc < ncols) scratch[oc] = (int)sout[lane] >> 16;
+                }
+            }
+            __syncwarp();
+        }
+        // the high half of lane 31's last register is G[len2][len1]; H = G - i - j
+        if (lane == 31)
+            p.scores[pair] = ((ncols > 0 && p.nstrips > 0) ? ((int)h[R - 1] >> 16) : 0) - p.len1 - p.len2;
+    }
+}
+
+}  // namespace nw

@@ -7,8 +7,8 @@
 // (message in nw_cuda_last_error()) when there is none.
 #include "../../include/nw_cuda.h"
 #include "nw_kernels.cuh"
-#include "nw_batch.cuh"
 #include "nw_packed.cuh"
+#include "nw_batch.cuh"
 
 #include <cooperative_groups.h>
 #include <algorithm>
@@ -93,6 +93,17 @@ BatchKernel batch_kernel(int R, bool generic)
     case 8: return generic ? nw::nw_batch_kernel<8, true> : nw::nw_batch_kernel<8, false>;
     case 16: return generic ? nw::nw_batch_kernel<16, true> : nw::nw_batch_kernel<16, false>;
     case 32: return generic ? nw::nw_batch_kernel<32, true> : nw::nw_batch_kernel<32, false>;
+    default: return nullptr;
+    }
+}
+
+BatchKernel batch16_kernel(int regs)
+{
+    switch (regs) {
+    case 2: return nw::nw_batch16_kernel<2>;
+    case 4: return nw::nw_batch16_kernel<4>;
+    case 8: return nw::nw_batch16_kernel<8>;
+    case 16: return nw::nw_batch16_kernel<16>;
     default: return nullptr;
     }
 }
@@ -842,6 +853,8 @@ struct nw_batch {
     int len1 = 0, len2 = 0;
     int R = 32, nstrips = 0, pad_top = 0, warps = 8, ctas = 0;
     bool generic = false, uploaded = false, ran = false;
+    bool packed = false;      // nw_batch16_kernel: at most four letters and G fits 15 bits
+    size_t scratch_words = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint8_t *d_S1 = nullptr, *d_S2 = nullptr;
@@ -869,14 +882,14 @@ extern "C" int nw_batch_destroy(nw_batch* b)
     return NW_OK;
 }
 
-static int batch_setup(nw_batch* b)
+// geometry + kernel choice; needs the alphabet, so it is called again after every upload
+static int batch_pick_kernel(nw_batch* b)
 {
     const DeviceState& d = g_dev[b->device];
     CK(cudaSetDevice(b->device));
-    CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&b->ev0));
-    CK(cudaEventCreate(&b->ev1));
-    int R = env_int("NW_CUDA_BATCH_R", 0);
+    const long long gmax = 3LL * std::min(b->len1, b->len2) + 64;
+    b->packed = !b->generic && gmax < 32000 && !env_int("NW_CUDA_NO_PACKED", 0);
+    int R = env_int("NW_CUDA_BATCH_R", 0);       // table rows per lane
     if (R == 0) {
         R = 32;
         while (R > 4 && b->len2 <= 32 * (R / 2)) R /= 2;      // smallest strip that still covers the pair in one pass
@@ -885,21 +898,37 @@ static int batch_setup(nw_batch* b)
     b->R = R;
     b->nstrips = (int)(((long long)b->len2 + 32LL * R - 1) / (32LL * R));
     b->pad_top = b->nstrips * 32 * R - b->len2;
-    b->warps = 8;
-    b->smem = sizeof(uint32_t) * nw::SMEM_WORDS_PER_WARP * (size_t)b->warps;
-    CK(cudaMalloc(&b->d_scores, sizeof(int32_t) * (size_t)std::max<long long>(b->npairs, 1)));
-    CK(cudaMalloc(&b->d_bitmap, 8 * sizeof(uint32_t)));
-    b->kernel = batch_kernel(b->R, false);
+    b->warps = b->packed ? 4 : 8;
+    b->kernel = b->packed ? batch16_kernel(R / 2) : batch_kernel(R, b->generic);
+    if (!b->kernel) return fail(NW_ERR_ARG, "no batch kernel for rows_per_lane=%d", R);
+    b->smem = sizeof(uint32_t) * (size_t)(b->packed ? nw::SMEM16_WORDS_PER_WARP : nw::SMEM_WORDS_PER_WARP) * (size_t)b->warps;
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b->kernel, b->warps * 32, b->smem));
     if (per_sm < 1) return fail(NW_ERR_CUDA, "batch kernel does not fit on an SM");
-    per_sm = std::min(per_sm, std::max(1, env_int("NW_CUDA_BATCH_CTAS_PER_SM", 2)));
+    const int want_per_sm = env_int("NW_CUDA_BATCH_CTAS_PER_SM", b->packed ? 4 : 2);
+    per_sm = std::min(per_sm, std::max(1, want_per_sm));
     long long want = (b->npairs + b->warps - 1) / b->warps;
     b->ctas = (int)std::max<long long>(1, std::min<long long>(want, (long long)d.sm_count * per_sm));
     b->scratch_pitch = ((long long)b->len1 + 63) & ~31LL;
-    if (b->nstrips > 1)
-        CK(cudaMalloc(&b->d_scratch, sizeof(int32_t) * (size_t)b->scratch_pitch * (size_t)b->ctas * (size_t)b->warps));
+    const size_t need = (b->nstrips > 1) ? (size_t)b->scratch_pitch * (size_t)b->ctas * (size_t)b->warps : 0;
+    if (need > b->scratch_words) {
+        if (b->d_scratch) CK(cudaFree(b->d_scratch));
+        b->d_scratch = nullptr;
+        CK(cudaMalloc(&b->d_scratch, sizeof(int32_t) * need));
+        b->scratch_words = need;
+    }
     return NW_OK;
+}
+
+static int batch_setup(nw_batch* b)
+{
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&b->ev0));
+    CK(cudaEventCreate(&b->ev1));
+    CK(cudaMalloc(&b->d_scores, sizeof(int32_t) * (size_t)std::max<long long>(b->npairs, 1)));
+    CK(cudaMalloc(&b->d_bitmap, 8 * sizeof(uint32_t)));
+    return batch_pick_kernel(b);
 }
 
 extern "C" int nw_batch_create(nw_batch** out, int device, int64_t npairs, int32_t len1, int32_t len2)
@@ -939,7 +968,8 @@ static int batch_scan(nw_batch* b)
     bitmap_to_seen(bm, seen);
     b->generic = !build_code(seen, b->code);
     if (env_int("NW_CUDA_GENERIC", 0)) b->generic = true;
-    b->kernel = batch_kernel(b->R, b->generic);
+    int rc = batch_pick_kernel(b);
+    if (rc) return rc;
     b->uploaded = true;
     return NW_OK;
 }
