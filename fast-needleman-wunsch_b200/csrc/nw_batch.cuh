@@ -165,9 +165,9 @@ __global__ void __launch_bounds__(128) nw_batch16_kernel(const BatchParams p)
                 }
                 __syncwarp();
                 if (cb >= 64 && cb + 31 < ncols)
-                    sweep16<R, false>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols);
+                    sweep16<R, false, false>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols);
                 else
-                    sweep16<R, true>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols);
+                    sweep16<R, true, false>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols);
                 __syncwarp();
                 if (s + 1 < p.nstrips) {
                     const int oc = cb - 63 + lane;

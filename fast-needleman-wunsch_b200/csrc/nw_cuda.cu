@@ -891,8 +891,10 @@ static int batch_pick_kernel(nw_batch* b)
     b->packed = !b->generic && gmax < 32000 && !env_int("NW_CUDA_NO_PACKED", 0);
     int R = env_int("NW_CUDA_BATCH_R", 0);       // table rows per lane
     if (R == 0) {
-        R = 32;
-        while (R > 4 && b->len2 <= 32 * (R / 2)) R /= 2;      // smallest strip that still covers the pair in one pass
+        // 32-bit kernel: the smallest strip that covers the pair in one pass.  Packed kernel: 8 registers (16 rows per
+        // lane) measured fastest on B200 -- more resident warps beat fewer passes (profiles/r01_batch_sweep.log)
+        R = b->packed ? 16 : 32;
+        while (R > 4 && b->len2 <= 32 * (R / 2)) R /= 2;
     }
     if (R != 4 && R != 8 && R != 16 && R != 32) return fail(NW_ERR_ARG, "batch rows_per_lane must be 4, 8, 16 or 32");
     b->R = R;
@@ -905,7 +907,7 @@ static int batch_pick_kernel(nw_batch* b)
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b->kernel, b->warps * 32, b->smem));
     if (per_sm < 1) return fail(NW_ERR_CUDA, "batch kernel does not fit on an SM");
-    const int want_per_sm = env_int("NW_CUDA_BATCH_CTAS_PER_SM", b->packed ? 4 : 2);
+    const int want_per_sm = env_int("NW_CUDA_BATCH_CTAS_PER_SM", b->packed ? 7 : 2);
     per_sm = std::min(per_sm, std::max(1, want_per_sm));
     long long want = (b->npairs + b->warps - 1) / b->warps;
     b->ctas = (int)std::max<long long>(1, std::min<long long>(want, (long long)d.sm_count * per_sm));

@@ -25,7 +25,9 @@ constexpr int SMEM16_WORDS_PER_WARP = 4 * RING_COPY_WORDS + 32 + 32;   // 4 ring
 // computed as  G[r] = max(P[r], up)  with the prefix maxima P[r] of the t[] off the chain): with one warp per scheduler
 // the kernel is bound by that latency, not by issue slots, so the R-1 extra max instructions are free.  The operand
 // vectors of the next 4 steps are loaded before the current 4 are computed (shared-memory latency off the chain too).
-template <int R, bool PRED>
+// LOWLAT = false (batch mode, several warps per scheduler hide the latency): the plain running max down the rows, 3R
+// instructions per step and nothing more.
+template <int R, bool PRED, bool LOWLAT = true>
 __device__ __forceinline__ void sweep16(uint32_t (&h)[R], uint32_t& dprev, const uint32_t (&sel)[R],
                                         const uint32_t upsel, const int src_lane, const uint32_t* __restrict__ ringm,
                                         const uint32_t* __restrict__ sin, uint32_t* sout, const int lane, const int cb,
@@ -62,11 +64,6 @@ __device__ __forceinline__ void sweep16(uint32_t (&h)[R], uint32_t& dprev, const
                     diag = h[r];
                 }
             }
-            // prefix maxima of t[0..r-1] (off the chain), then G[r] = max3(t[r], P[r-1], up): one instruction per row
-            uint32_t P[R];
-            P[0] = t[0];
-#pragma unroll
-            for (int r = 1; r + 1 < R; ++r) P[r] = __vmaxs2(t[r], P[r - 1]);
             const uint32_t up0 = prmt(s, tn[kk], upsel);       // {low: row above at col c, high: row above at col c-32}
             dprev = up0;
             uint32_t mask = 0xffffffffu;
@@ -75,14 +72,32 @@ __device__ __forceinline__ void sweep16(uint32_t (&h)[R], uint32_t& dprev, const
                 mask = ((unsigned)col < (unsigned)ncols ? 0x0000ffffu : 0u) |
                        ((unsigned)(col - 32) < (unsigned)ncols ? 0xffff0000u : 0u);
             }
-            {   // the last row first: it feeds the next step's shuffle
-                const uint32_t g = (R > 1) ? __vimax3_s16x2(t[R - 1], P[R > 1 ? R - 2 : 0], up0) : __vmaxs2(t[0], up0);
-                h[R - 1] = PRED ? ((g & mask) | (h[R - 1] & ~mask)) : g;
-            }
+            if (LOWLAT) {
+                // prefix maxima of t[0..r-1] (off the chain), then G[r] = max3(t[r], P[r-1], up): one instruction per row
+                uint32_t P[R];
+                P[0] = t[0];
 #pragma unroll
-            for (int r = 0; r + 1 < R; ++r) {
-                const uint32_t g = (r == 0) ? __vmaxs2(t[0], up0) : __vimax3_s16x2(t[r], P[r - 1], up0);
-                h[r] = PRED ? ((g & mask) | (h[r] & ~mask)) : g;
+                for (int r = 1; r + 1 < R; ++r) P[r] = __vmaxs2(t[r], P[r - 1]);
+                {   // the last row first: it feeds the next step's shuffle
+                    const uint32_t g = (R > 1) ? __vimax3_s16x2(t[R - 1], P[R > 1 ? R - 2 : 0], up0) : __vmaxs2(t[0], up0);
+                    h[R - 1] = PRED ? ((g & mask) | (h[R - 1] & ~mask)) : g;
+                }
+#pragma unroll
+                for (int r = 0; r + 1 < R; ++r) {
+                    const uint32_t g = (r == 0) ? __vmaxs2(t[0], up0) : __vimax3_s16x2(t[r], P[r - 1], up0);
+                    h[r] = PRED ? ((g & mask) | (h[r] & ~mask)) : g;
+                }
+            } else {
+                uint32_t g = up0;                               // running max; every second link is a 3-input max
+#pragma unroll
+                for (int r = 0; r < R; r += 2) {
+                    const uint32_t ga = __vmaxs2(t[r], g);
+                    uint32_t gb = ga;
+                    if (r + 1 < R) gb = __vimax3_s16x2(t[r + 1], t[r], g);
+                    h[r] = PRED ? ((ga & mask) | (h[r] & ~mask)) : ga;
+                    if (r + 1 < R) h[r + 1] = PRED ? ((gb & mask) | (h[r + 1] & ~mask)) : gb;
+                    g = gb;
+                }
             }
 #ifndef NW_DBG_NO_STS
             if (lane == 31) sout[k] = h[R - 1];

@@ -1,4 +1,3 @@
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench2.json 2> gpurun_out/bench2.err
-python bench.py --workload mid --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain_mid.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:nw_strip16 -s 3 -c 1 -o gpurun_out/prof_r01_strip16_mid python bench.py --workload mid --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_mid.log 2>&1
-python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain_64gb.log 2>&1 && ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_r01_v2_64gb.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_64gb.log 2>&1
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench2_ref.json 2>&1
+for r in 8 16; do for c in 6 7 8; do echo "R=$r ctas/sm=$c" >> gpurun_out/batch2.log; NW_CUDA_BATCH_R=$r NW_CUDA_BATCH_CTAS_PER_SM=$c python bench.py --workload batch --steps 3 --warmup 2 --batch-pairs 200000 >> gpurun_out/batch2.log 2>&1; done; done
+echo "default 1M pairs" >> gpurun_out/batch2.log
+python bench.py --workload batch --steps 3 --warmup 2 --batch-pairs 1000000 >> gpurun_out/batch2.log 2>&1
