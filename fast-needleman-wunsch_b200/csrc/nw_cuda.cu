@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <vector>
 
@@ -82,6 +83,26 @@ StripKernel strip16_kernel(int regs)
     case 4: return nw::nw_strip16_kernel<4>;
     case 8: return nw::nw_strip16_kernel<8>;
     default: return nullptr;
+    }
+}
+
+StripKernel full16_kernel(int regs)
+{
+    switch (regs) {
+    case 1: return nw::nw_full16_kernel<1>;
+    case 2: return nw::nw_full16_kernel<2>;
+    case 4: return nw::nw_full16_kernel<4>;
+    case 8: return nw::nw_full16_kernel<8>;
+    default: return nullptr;
+    }
+}
+int full16_smem_words(int regs)
+{
+    switch (regs) {
+    case 1: return (nw::SMEM16F_WORDS_PER_WARP(1) + 3) & ~3;
+    case 2: return (nw::SMEM16F_WORDS_PER_WARP(2) + 3) & ~3;
+    case 4: return (nw::SMEM16F_WORDS_PER_WARP(4) + 3) & ~3;
+    default: return (nw::SMEM16F_WORDS_PER_WARP(8) + 3) & ~3;
     }
 }
 
@@ -163,6 +184,11 @@ struct nw_plan {
     int32_t *d_last_row = nullptr, *d_last_col = nullptr, *d_score = nullptr, *d_tmp_row = nullptr;
     size_t smem = 0;
     StripKernel kernel = nullptr;
+    // packed full-table mode: pass 1 (kernel above, with snapshots) + pass 2 (tile replay with coalesced table stores)
+    StripKernel kernel2 = nullptr;
+    uint32_t* d_snap = nullptr;
+    size_t snap_words = 0, smem2 = 0;
+    int tile_blocks = 32, ntiles = 1, ctas2 = 0, warps2 = 5;
 };
 
 static int ensure_device(int device)
@@ -272,7 +298,7 @@ extern "C" int nw_plan_destroy(nw_plan* p)
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->ipc_mailbox) cudaIpcCloseMemHandle(p->ipc_mailbox);
     void* bufs[] = {p->d_s1, p->d_s2, p->d_wq, p->d_rsel, p->d_bitmap, p->d_brow, p->d_mailbox, p->d_rcol_local,
-                    p->d_table, p->d_dump, p->d_last_row, p->d_last_col, p->d_score, p->d_tmp_row};
+                    p->d_table, p->d_dump, p->d_snap, p->d_last_row, p->d_last_col, p->d_score, p->d_tmp_row};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (p->ev0) cudaEventDestroy(p->ev0);
@@ -318,7 +344,7 @@ static int plan_alloc(nw_plan* p, const nw_tuning* tuning)
     CK(cudaMemset(p->d_rcol_local, 0, sizeof(int2) * 2 * (size_t)p->mpitch));
     p->rcol_target = p->d_rcol_local;
     if (p->mode == NW_MODE_FULL) {
-        p->tpitch = (long long)nc + 1;
+        p->tpitch = ((long long)nc + 1 + 7) & ~7LL;      // rows start on a 32-byte sector: the table stores need it
         CK(cudaMalloc(&p->d_table, sizeof(int32_t) * (size_t)p->tpitch * ((size_t)n2 + 1)));
         CK(cudaMalloc(&p->d_dump, sizeof(int32_t) * (size_t)p->tpitch));
     }
@@ -334,7 +360,8 @@ static int plan_pick_kernel(nw_plan* p)
 {
     const DeviceState& d = g_dev[p->device];
     CK(cudaSetDevice(p->device));
-    p->packed = !p->generic && p->mode == NW_MODE_BOUNDARY && !env_int("NW_CUDA_NO_PACKED", 0) && p->R_req != 1;
+    p->packed = !p->generic && !env_int("NW_CUDA_NO_PACKED", 0) && p->R_req != 1 &&
+                (p->mode == NW_MODE_BOUNDARY || !env_int("NW_CUDA_NO_PACKED_FULL", 0));
     int R = p->R_req;
     if (R == 0) R = p->packed ? choose_rows_per_lane_packed(p->n2, p->ncols, d.sm_count)
                               : choose_rows_per_lane(p->n2, p->ncols, d.sm_count);
@@ -366,6 +393,30 @@ static int plan_pick_kernel(nw_plan* p)
         p->smem = sizeof(uint32_t) * nw::SMEM_WORDS_PER_WARP * (size_t)p->warps;
     }
     if (!p->kernel) return fail(NW_ERR_ARG, "no kernel for rows_per_lane=%d (%s)", R, p->packed ? "packed" : "32-bit");
+    p->kernel2 = nullptr;
+    if (p->packed && p->mode == NW_MODE_FULL) {
+        const int regs = R / 2;
+        const int nblocks = (p->ncols + 63 + 31) >> 5;
+        p->tile_blocks = std::max(2, env_int("NW_CUDA_TILE_BLOCKS", 32));
+        p->ntiles = std::max(1, (nblocks + p->tile_blocks - 1) / p->tile_blocks);
+        const size_t need = (size_t)std::max(p->nstrips, 1) * (size_t)p->ntiles * 32u * (size_t)(regs + 2);
+        if (need > p->snap_words) {
+            if (p->d_snap) CK(cudaFree(p->d_snap));
+            p->d_snap = nullptr;
+            CK(cudaMalloc(&p->d_snap, sizeof(uint32_t) * need));
+            p->snap_words = need;
+        }
+        p->kernel2 = full16_kernel(regs);
+        p->warps2 = std::max(1, std::min(8, env_int("NW_CUDA_FULL_WARPS", 5)));
+        p->smem2 = sizeof(uint32_t) * (size_t)full16_smem_words(regs) * (size_t)p->warps2;
+        CK(cudaFuncSetAttribute((const void*)p->kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem2));
+        int per_sm2 = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, p->kernel2, p->warps2 * 32, p->smem2));
+        if (per_sm2 < 1) return fail(NW_ERR_CUDA, "full-table pass-2 kernel does not fit on an SM");
+        const long long ntasks = (long long)p->nstrips * p->ntiles;
+        p->ctas2 = (int)std::max<long long>(1, std::min<long long>((ntasks + p->warps2 - 1) / p->warps2,
+                                                                     (long long)d.sm_count * per_sm2));
+    }
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p->kernel, p->warps * 32, p->smem));
     if (per_sm < 1) return fail(NW_ERR_CUDA, "strip kernel does not fit on an SM (warps=%d)", p->warps);
@@ -566,8 +617,16 @@ static int plan_enqueue(nw_plan* p)
         sp.halo_sys = p->halo_peer ? 1 : 0;
         sp.rcol_sys = p->rcol_peer ? 1 : 0;
         sp.ack_in = (p->rcol_target != p->d_rcol_local) ? (const int*)(p->rcol_target + 2 * p->mpitch) : nullptr;
+        sp.snap = p->kernel2 ? p->d_snap : nullptr;
+        sp.tile_blocks = p->tile_blocks;
+        sp.ntiles = p->ntiles;
         void* args[] = {&sp};
         CK(cudaLaunchCooperativeKernel((const void*)p->kernel, dim3(p->ctas), dim3(p->warps * 32), args, p->smem, p->stream));
+        if (p->kernel2 && !env_int("NW_CUDA_DBG_SKIP_PASS2", 0)) {           // pass 2: every tile of every strip at once, table stores as 128-byte row segments
+            sp.ack_in = nullptr;
+            p->kernel2<<<p->ctas2, p->warps2 * 32, p->smem2, p->stream>>>(sp);
+            CK(cudaGetLastError());
+        }
     }
     {
         const int2* brow_last = (p->n2 > 0 && have_cells) ? p->d_brow + (long long)(p->nstrips - 1) * p->pitch : nullptr;
@@ -650,7 +709,8 @@ extern "C" int nw_plan_launches_per_run(nw_plan* p, int* n)
 {
     if (!p || !n) return fail(NW_ERR_ARG, "bad argument");
     const bool have_cells = p->ncols > 0 && p->n2 > 0;
-    *n = (have_cells ? 1 : 0) + 1 + (p->mode == NW_MODE_FULL ? 1 + ((!have_cells && p->n2 > 0) ? 1 : 0) : 0);
+    *n = (have_cells ? 1 : 0) + 1 + (p->mode == NW_MODE_FULL ? 1 + ((!have_cells && p->n2 > 0) ? 1 : 0) : 0) +
+         ((have_cells && p->kernel2) ? 1 : 0);
     return NW_OK;
 }
 
@@ -685,6 +745,126 @@ extern "C" int nw_plan_last_col(nw_plan* p, int32_t* last_col)
     return NW_OK;
 }
 
+// ---- table delivery to a PAGEABLE host buffer -------------------------------------------------------------------------
+// The reference's driver owns the table as `new int[size]` (src/common/driver.cpp:22): a plain cudaMemcpy into it runs
+// at a few GB/s.  Instead the table goes device -> pinned staging (DMA at PCIe rate) -> destination (several host
+// threads), double-buffered so that the DMA of chunk k+1 overlaps the host copy of chunk k.
+namespace {
+struct Staging {
+    void* buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    size_t bytes = 0;
+    int device = -1;
+};
+Staging g_stage;
+std::mutex g_stage_mu;
+
+void parallel_memcpy(char* dst, const char* src, size_t n, int nthreads)
+{
+    if (n < (4u << 20) || nthreads <= 1) {
+        memcpy(dst, src, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = ((n / nthreads) + 4095) & ~(size_t)4095;
+    for (int t = 1; t < nthreads; ++t) {
+        const size_t off = per * t;
+        if (off >= n) break;
+        th.emplace_back([=] { memcpy(dst + off, src + off, std::min(per, n - off)); });
+    }
+    memcpy(dst, src, std::min(per, n));
+    for (auto& x : th) x.join();
+}
+
+bool host_pointer_is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+}  // namespace
+
+static int ensure_staging(int device)       // caller holds g_stage_mu
+{
+    const size_t chunk = (size_t)std::max(1, env_int("NW_CUDA_STAGE_MB", 32)) << 20;
+    if (g_stage.bytes == chunk && g_stage.device == device) return NW_OK;
+    CK(cudaSetDevice(device));
+    for (int i = 0; i < 2; ++i) {
+        if (g_stage.buf[i]) cudaFreeHost(g_stage.buf[i]);
+        if (g_stage.ev[i]) cudaEventDestroy(g_stage.ev[i]);
+        g_stage.buf[i] = nullptr;
+        g_stage.ev[i] = nullptr;
+    }
+    g_stage.bytes = 0;
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaHostAlloc(&g_stage.buf[i], chunk, cudaHostAllocDefault));
+        CK(cudaEventCreateWithFlags(&g_stage.ev[i], cudaEventDisableTiming));
+    }
+    g_stage.bytes = chunk;
+    g_stage.device = device;
+    return NW_OK;
+}
+
+// rows x width bytes from device (pitch dpitch) to host (pitch hpitch), host pageable
+static int staged_d2h_2d(nw_plan* p, char* dst, size_t hpitch, const char* src, size_t dpitch, size_t width, size_t rows)
+{
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    int rc0 = ensure_staging(p->device);
+    if (rc0) return rc0;
+    const size_t chunk = g_stage.bytes;
+    const int nthreads = std::max(1, std::min(env_int("NW_CUDA_COPY_THREADS", 8), (int)std::thread::hardware_concurrency()));
+    const bool flat = (width == hpitch && width == dpitch);
+    // unit of work: a run of whole rows (or a byte range when the table is contiguous on both sides)
+    const size_t total = flat ? width * rows : rows;
+    const size_t step = flat ? chunk : std::max<size_t>(1, chunk / width);
+    size_t done_issue = 0, done_copy = 0;
+    int slot = 0;
+    size_t pend_off[2] = {0, 0}, pend_n[2] = {0, 0};
+    bool pending[2] = {false, false};
+    while (done_copy < total) {
+        if (done_issue < total && !pending[slot]) {
+            const size_t n = std::min(step, total - done_issue);
+            if (flat) CK(cudaMemcpyAsync(g_stage.buf[slot], src + done_issue, n, cudaMemcpyDeviceToHost, p->stream));
+            else CK(cudaMemcpy2DAsync(g_stage.buf[slot], width, src + done_issue * dpitch, dpitch, width, n,
+                                      cudaMemcpyDeviceToHost, p->stream));
+            CK(cudaEventRecord(g_stage.ev[slot], p->stream));
+            pend_off[slot] = done_issue;
+            pend_n[slot] = n;
+            pending[slot] = true;
+            done_issue += n;
+            slot ^= 1;
+            if (done_issue < total && !pending[slot]) continue;      // keep two DMAs in flight
+        }
+        // retire the older one
+        const int o = pending[slot] ? slot : slot ^ 1;
+        CK(cudaEventSynchronize(g_stage.ev[o]));
+        if (flat) parallel_memcpy(dst + pend_off[o], (const char*)g_stage.buf[o], pend_n[o], nthreads);
+        else {
+            const char* sb = (const char*)g_stage.buf[o];
+            const size_t r0 = pend_off[o], nr = pend_n[o];
+            if (nr * width < (4u << 20)) {
+                for (size_t r = 0; r < nr; ++r) memcpy(dst + (r0 + r) * hpitch, sb + r * width, width);
+            } else {
+                std::vector<std::thread> th;
+                const size_t per = (nr + nthreads - 1) / nthreads;
+                for (int t = 0; t < nthreads; ++t) {
+                    const size_t a = per * t, b = std::min(nr, a + per);
+                    if (a >= b) break;
+                    th.emplace_back([=] { for (size_t r = a; r < b; ++r) memcpy(dst + (r0 + r) * hpitch, sb + r * width, width); });
+                }
+                for (auto& x : th) x.join();
+            }
+        }
+        done_copy += pend_n[o];
+        pending[o] = false;
+        slot = o;
+    }
+    return NW_OK;
+}
+
 extern "C" int nw_plan_table_to_host(nw_plan* p, int32_t* table)
 {
     if (!p || !table) return fail(NW_ERR_ARG, "bad argument");
@@ -696,11 +876,22 @@ extern "C" int nw_plan_table_to_host(nw_plan* p, int32_t* table)
     const int skip = (p->part > 0) ? 1 : 0;
     const size_t width = sizeof(int32_t) * ((size_t)p->ncols + 1 - skip);
     if (width == 0) return NW_OK;
+    const size_t rows = (size_t)p->n2 + 1;
+    const bool pinned = host_pointer_is_pinned(table);
+    if (!pinned && width * rows >= (8u << 20) && !env_int("NW_CUDA_NO_STAGING", 0)) {
+        CK(cudaStreamSynchronize(p->stream));
+        if (p->nparts == 1)
+            return staged_d2h_2d(p, (char*)table, host_pitch, (const char*)p->d_table,
+                                 sizeof(int32_t) * (size_t)p->tpitch, host_pitch, rows);
+        return staged_d2h_2d(p, (char*)(table + p->jstart + skip), host_pitch, (const char*)(p->d_table + skip),
+                             sizeof(int32_t) * (size_t)p->tpitch, width, rows);
+    }
     if (p->nparts == 1) {
-        CK(cudaMemcpyAsync(table, p->d_table, host_pitch * ((size_t)p->n2 + 1), cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaMemcpy2DAsync(table, host_pitch, p->d_table, sizeof(int32_t) * (size_t)p->tpitch, host_pitch, rows,
+                             cudaMemcpyDeviceToHost, p->stream));
     } else {
         CK(cudaMemcpy2DAsync(table + p->jstart + skip, host_pitch, p->d_table + skip, sizeof(int32_t) * (size_t)p->tpitch,
-                             width, (size_t)p->n2 + 1, cudaMemcpyDeviceToHost, p->stream));
+                             width, rows, cudaMemcpyDeviceToHost, p->stream));
     }
     CK(cudaStreamSynchronize(p->stream));
     return NW_OK;
@@ -761,6 +952,10 @@ extern "C" int nw_cuda_init(int device)
     if (rc == NW_OK) rc = nw_plan_score(p, &score);
     nw_plan_destroy(p);
     if (rc == NW_OK && score != 40) return fail(NW_ERR_CUDA, "self-test failed: score %d, expected 40", score);
+    if (rc == NW_OK) {      // pinned staging for table delivery, so the first timed call does not allocate it
+        std::lock_guard<std::mutex> lk(g_stage_mu);
+        rc = ensure_staging(device);
+    }
     return rc;
 }
 

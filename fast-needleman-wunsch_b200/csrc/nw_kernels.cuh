@@ -77,6 +77,10 @@ struct StripParams {
     int halo_sys;           // halo written by a peer device: poll with system scope
     int rcol_sys;           // rcol is peer memory: store with system scope
     // back-pressure of a column-strip pipeline (mailboxes are double-buffered by epoch parity):
+    // full-table mode with the packed kernels (nw_packed.cuh): pass 1 snapshots / pass 2 tiles
+    uint32_t* snap;         // nstrips x ntiles x 32*(R+2) words, or nullptr
+    int tile_blocks;        // 32-column blocks per tile
+    int ntiles;             // tiles per strip
     const int* ack_in;      // producer side: the consumer's "finished epoch" word (in the consumer's mailbox
                             // allocation, possibly peer memory); the kernel waits for ack >= epoch - 2
 };

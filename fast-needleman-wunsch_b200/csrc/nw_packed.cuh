@@ -18,6 +18,7 @@
 
 namespace nw {
 
+constexpr int TILE_ROW_WORDS = 40;     // full-table pass 2: 8 carried-over columns + the 32 columns of the current block
 constexpr int RING_COPY_WORDS = 136;                       // 128-column ring + 8 words of bank skew per copy
 constexpr int SMEM16_WORDS_PER_WARP = 4 * RING_COPY_WORDS + 32 + 32;   // 4 ring copies + top inputs + bottom outputs
 
@@ -27,11 +28,13 @@ constexpr int SMEM16_WORDS_PER_WARP = 4 * RING_COPY_WORDS + 32 + 32;   // 4 ring
 // vectors of the next 4 steps are loaded before the current 4 are computed (shared-memory latency off the chain too).
 // LOWLAT = false (batch mode, several warps per scheduler hide the latency): the plain running max down the rows, 3R
 // instructions per step and nothing more.
-template <int R, bool PRED, bool LOWLAT = true>
+// TILE = true (pass 2 of full-table mode): every step also deposits the packed registers into this lane's slab of a
+// shared-memory tile ([register][step], lane pitch odd => conflict-free), which the warp then writes out row by row.
+template <int R, bool PRED, bool LOWLAT = true, bool TILE = false>
 __device__ __forceinline__ void sweep16(uint32_t (&h)[R], uint32_t& dprev, const uint32_t (&sel)[R],
                                         const uint32_t upsel, const int src_lane, const uint32_t* __restrict__ ringm,
                                         const uint32_t* __restrict__ sin, uint32_t* sout, const int lane, const int cb,
-                                        const int ncols)
+                                        const int ncols, uint32_t* tile_lane = nullptr)
 {
     const int i0 = cb - lane + (lane & 3);      // ring index (before & 127) of this lane's low column at k = 0; 4 | i0
     uint4 clo = *reinterpret_cast<const uint4*>(ringm + (i0 & 127));
@@ -102,6 +105,10 @@ __device__ __forceinline__ void sweep16(uint32_t (&h)[R], uint32_t& dprev, const
 #ifndef NW_DBG_NO_STS
             if (lane == 31) sout[k] = h[R - 1];
 #endif
+            if (TILE) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) tile_lane[r * TILE_ROW_WORDS + 8 + k] = h[r];
+            }
         }
     }
 }
@@ -216,6 +223,15 @@ __device__ __forceinline__ void run_strip16(const StripParams& p, const int s, c
                 base += D;
             }
         }
+        // full-table mode, pass 1: snapshot of the warp's (skewed) register state every `tile_blocks` blocks, from which
+        // pass 2 replays the blocks of a tile independently of every other tile
+        if (p.snap != nullptr && ((b + 1) % p.tile_blocks) == 0 && b + 1 < nblocks) {
+            uint32_t* sp = p.snap + ((long long)s * p.ntiles + (b + 1) / p.tile_blocks) * (long long)(32 * (R + 2));
+#pragma unroll
+            for (int r = 0; r < R; ++r) sp[r * 32 + lane] = h[r];
+            sp[R * 32 + lane] = dprev;
+            sp[(R + 1) * 32 + lane] = (uint32_t)base;
+        }
     }
 
     // right boundary column of this lane's rows (absolute G)
@@ -254,6 +270,236 @@ __global__ void __launch_bounds__(512) nw_strip16_kernel(const StripParams p)
         __syncthreads();
     }
     for (int s = slot; s < p.nstrips; s += nslots) run_strip16<R>(p, s, lane, smem);
+}
+
+// ---- full-table mode, pass 2 ------------------------------------------------------------------------------------------
+// Tile (s, m) = blocks [m*tile_blocks, (m+1)*tile_blocks) of strip s, replayed from pass 1's snapshot (m > 0) or from the
+// strip's initial state (m = 0) with the top boundary row read from brow (complete after pass 1).  Tiles are independent,
+// so the whole GPU works on them at once and the kernel is bound by the table stores: each block's cells go through a
+// shared-memory tile and leave as 128-byte row segments, H = G - i - j (reference layout: src/serial/serial.cpp:31).
+__host__ __device__ constexpr int TILE_LANE_PITCH(int R) { return R * TILE_ROW_WORDS + 1; }
+__host__ __device__ constexpr int SMEM16F_WORDS_PER_WARP(int R) { return SMEM16_WORDS_PER_WARP + 32 * TILE_LANE_PITCH(R) + 3; }
+
+template <int R>
+__global__ void __launch_bounds__(256) nw_full16_kernel(const StripParams p)
+{
+    extern __shared__ __align__(16) uint32_t nw_smem[];
+    constexpr int SH = 64 * R;
+    constexpr int WORDS = (SMEM16F_WORDS_PER_WARP(R) + 3) & ~3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint32_t* ring = nw_smem + warp * WORDS;
+    uint32_t* sin = ring + 4 * RING_COPY_WORDS;
+    uint32_t* sout = sin + 32;
+    uint32_t* tile = sout + 32;
+    uint32_t* tile_lane = tile + lane * TILE_LANE_PITCH(R);
+    const uint32_t* ringm = ring + (lane & 3) * RING_COPY_WORDS;
+    const int ncols = p.ncols;
+    const int nblocks = (ncols + 63 + 31) >> 5;
+    const uint32_t upsel = (lane == 0) ? 0x1054u : 0x3210u;
+    const int src_lane = (lane + 31) & 31;
+    const long long ntasks = (long long)p.nstrips * p.ntiles;
+
+    for (long long task = (long long)blockIdx.x * nwarps + warp; task < ntasks; task += (long long)gridDim.x * nwarps) {
+        const int s = (int)(task / p.ntiles), m = (int)(task - (long long)s * p.ntiles);
+        const int i_lo = s * SH + lane * R - p.pad_top;      // table row just above the low half's first row
+        const int i_hi = i_lo + 32 * R;
+        uint32_t sel[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) sel[r] = p.rsel[(s * 32 + lane) * R + r];
+
+        int base = 0;
+        uint32_t h[R];
+        uint32_t dprev = 0;
+        if (m > 0) {
+            const uint32_t* sp = p.snap + ((long long)s * p.ntiles + m) * (long long)(32 * (R + 2));
+#pragma unroll
+            for (int r = 0; r < R; ++r) h[r] = sp[r * 32 + lane];
+            dprev = sp[R * 32 + lane];
+            base = (int)sp[(R + 1) * 32 + lane];
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) h[r] = 0;
+            if (p.halo != nullptr) {
+                int lo[R + 1], hi[R + 1];
+                int mn = 0x7fffffff;
+#pragma unroll
+                for (int r = -1; r < R; ++r) {
+                    const int a = i_lo + 1 + r, b = i_hi + 1 + r;
+                    lo[r + 1] = (a >= 1) ? p.halo[a].y : 0;
+                    hi[r + 1] = (b >= 1) ? p.halo[b].y : 0;
+                    mn = min(mn, min(lo[r + 1], hi[r + 1]));
+                }
+                base = max(__reduce_min_sync(FULL_MASK, mn) - 8, 0);
+                dprev = ((uint32_t)(lo[0] - base) & 0xffffu) | ((uint32_t)(hi[0] - base) << 16);
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    h[r] = ((uint32_t)(lo[r + 1] - base) & 0xffffu) | ((uint32_t)(hi[r + 1] - base) << 16);
+            }
+            // table column 0 of this lane's rows: the left boundary (serial.cpp:17 / mpi-vert.cpp:57-59)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int a = i_lo + 1 + r, b = i_hi + 1 + r;
+                if (a >= 1) p.table[(long long)a * p.tpitch] = (int)(short)(h[r] & 0xffffu) + base - a - p.jstart;
+                if (b >= 1) p.table[(long long)b * p.tpitch] = ((int)h[r] >> 16) + base - b - p.jstart;
+            }
+        }
+
+        const int2* tin = p.brow + (long long)(s - 1) * p.pitch;
+        const int b0 = m * p.tile_blocks, b1 = min(nblocks, b0 + p.tile_blocks);
+        const uint32_t* wq = p.wq;
+        // ring contents a resumed tile still needs: columns [cb-96, cb) of its first block
+        if (m > 0) {
+            const int cb = b0 << 5;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int c = cb - 96 + 32 * q + lane;
+                const uint32_t w = wq[c];               // c >= -WQ_PAD always holds here (cb >= 32 * tile_blocks >= 64)
+#pragma unroll
+                for (int mm = 0; mm < 4; ++mm) ring[mm * RING_COPY_WORDS + ((c + mm) & 127)] = w;
+            }
+        }
+        uint32_t wnext = wq[min((b0 << 5) + lane, ncols + WQ_PAD - 1)];
+        int pre = 0;                                        // top boundary row, one block ahead
+        if (s > 0 && (b0 << 5) + lane < ncols) pre = tin[(b0 << 5) + lane + 1].y;
+        const long long tpitch = p.tpitch;
+        int32_t* const table = p.table;
+        for (int b = b0; b < b1; ++b) {
+            const int cb = b << 5;
+#pragma unroll
+            for (int mm = 0; mm < 4; ++mm) ring[mm * RING_COPY_WORDS + ((cb + lane + mm) & 127)] = wnext;
+            {
+                const int nc = cb + 32 + lane;
+                wnext = wq[nc < ncols + WQ_PAD ? nc : ncols + WQ_PAD - 1];
+            }
+            if (cb < ncols) {
+                sin[lane] = (uint32_t)(pre - base) & 0xffffu;
+                pre = 0;
+                if (s > 0 && cb + 32 + lane < ncols) pre = tin[cb + 32 + lane + 1].y;
+            }
+            __syncwarp();
+            const bool interior = cb >= 64 && cb + 31 < ncols;
+            if (interior)
+                sweep16<R, false, false, true>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols, tile_lane);
+            else
+                sweep16<R, true, false, true>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols, tile_lane);
+            __syncwarp();
+            // write-out.  Slab row (L, r) holds, at position p, the packed cells of table column cb - L - 7 + p (low half;
+            // the high half is 32 columns to the left and 32*R rows down): positions 0..7 are carried over from the
+            // previous block, 8..39 are this block's steps.  Stores must be 32-byte-sector aligned to reach HBM speed
+            // (misaligned 128-byte segments run at a third of it, tools/ubench/wr.cu), so in a run of interior blocks
+            // every slab writes the aligned 32-column window [d, d+32), d = (L + 7) & 7; the few columns before the first
+            // window / after the last one of a run are written as partial heads / tails.
+            {
+                const int row0 = s * SH - p.pad_top + 1;                 // table row of virtual lane 0, register 0
+                const bool rows_real = (s > 0) || (p.pad_top == 0);
+                const bool fast = interior && rows_real;
+                if (fast) {
+                    const bool first = (b == b0) || !(cb - 32 >= 64);
+                    const bool last = (b + 1 == b1) || !(cb + 32 + 31 < ncols);
+                    // H = stored + base - i - j_table, j_table = jstart + (cb - L - 7 + p)
+                    const int o0 = base - p.jstart - cb + 7 - row0;
+                    const long long hi_off = (long long)(32 * R) * tpitch - 32;
+                    constexpr int UNR = (R >= 8) ? 2 : (R == 4 ? 4 : 8);
+#pragma unroll 1
+                    for (int L0 = 0; L0 < 32; L0 += UNR) {
+                        uint32_t w[UNR][R];
+                        int pos[UNR];
+#pragma unroll
+                        for (int u = 0; u < UNR; ++u) {
+                            const int L = L0 + u, d = (L + 7) & 7;
+                            pos[u] = d + lane;
+                            if (first && pos[u] < 8) pos[u] = -1;                 // before this run's first own column
+#pragma unroll
+                            for (int r = 0; r < R; ++r)
+                                w[u][r] = tile[L * TILE_LANE_PITCH(R) + r * TILE_ROW_WORDS + (pos[u] < 0 ? 0 : pos[u])];
+                        }
+#pragma unroll
+                        for (int u = 0; u < UNR; ++u) {
+                            const int L = L0 + u;
+                            if (pos[u] >= 0) {
+                                int32_t* q = table + (long long)(row0 + L * R) * tpitch + (cb - L - 7 + pos[u]);
+                                const int o = o0 + L - L * R - pos[u];
+#pragma unroll
+                                for (int r = 0; r < R; ++r) {
+                                    q[(long long)r * tpitch] = (int)(short)(w[u][r] & 0xffffu) + o - r;
+                                    q[(long long)r * tpitch + hi_off] = ((int)w[u][r] >> 16) + o + (32 - 32 * R) - r;
+                                }
+                            }
+                        }
+                    }
+                    if (last) {                                  // tail: positions [d + 32, 40) of every slab
+                        for (int L = 0; L < 32; ++L) {
+                            const int pp = ((L + 7) & 7) + 32 + lane;
+                            if (pp < TILE_ROW_WORDS) {
+                                int32_t* q = table + (long long)(row0 + L * R) * tpitch + (cb - L - 7 + pp);
+                                const int o = o0 + L - L * R - pp;
+#pragma unroll
+                                for (int r = 0; r < R; ++r) {
+                                    const uint32_t ww = tile[L * TILE_LANE_PITCH(R) + r * TILE_ROW_WORDS + pp];
+                                    q[(long long)r * tpitch] = (int)(short)(ww & 0xffffu) + o - r;
+                                    q[(long long)r * tpitch + hi_off] = ((int)ww >> 16) + o + (32 - 32 * R) - r;
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    for (int L = 0; L < 32; ++L) {
+                        const uint32_t* tl = tile + L * TILE_LANE_PITCH(R) + 8 + lane;
+                        const int clo = cb + lane - L, chi = clo - 32;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const uint32_t w = tl[r * TILE_ROW_WORDS];
+                            const int ilo = row0 + L * R + r, ihi = ilo + 32 * R;
+                            if (ilo >= 1 && clo >= 0 && clo < ncols)
+                                table[(long long)ilo * tpitch + clo + 1] =
+                                    (int)(short)(w & 0xffffu) + base - ilo - (p.jstart + clo + 1);
+                            if (ihi >= 1 && chi >= 0 && chi < ncols)
+                                table[(long long)ihi * tpitch + chi + 1] = ((int)w >> 16) + base - ihi - (p.jstart + chi + 1);
+                        }
+                    }
+                }
+                __syncwarp();
+                // carry the last 8 columns of every slab row over to positions 0..7 for the next block
+                if (fast) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        uint32_t c8[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) c8[q] = tile_lane[r * TILE_ROW_WORDS + 32 + q];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) tile_lane[r * TILE_ROW_WORDS + q] = c8[q];
+                    }
+                }
+            }
+            __syncwarp();
+            if ((b & 31) == 31) {                            // the same re-basing decisions as pass 1
+                uint32_t mm = dprev;
+#pragma unroll
+                for (int r = 0; r < R; ++r) mm = __vmins2(mm, h[r]);
+                int mv = min((int)(short)(mm & 0xffffu), (int)mm >> 16);
+                mv = __reduce_min_sync(FULL_MASK, mv);
+                const int D = mv - 8;
+                if (D > 0) {
+                    const uint32_t Dp = (uint32_t)D * 0x10001u;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) h[r] -= Dp;
+                    dprev -= Dp;
+                    base += D;
+                    // the carried-over columns in the tile are in the old base too; they may be smaller than D, so
+                    // subtract half by half
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const uint32_t w = tile_lane[r * TILE_ROW_WORDS + q];
+                            const int lo = (int)(short)(w & 0xffffu) - D, hi = ((int)w >> 16) - D;
+                            tile_lane[r * TILE_ROW_WORDS + q] = ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16);
+                        }
+                }
+            }
+        }
+        __syncwarp();
+    }
 }
 
 }  // namespace nw

@@ -25,7 +25,7 @@ def test_fixture_full_table(gpu, oracle, name):
 
 
 @pytest.mark.parametrize("name", sorted(GOLDEN["synthetic"]))
-@pytest.mark.parametrize("R", [0, 1, 2, 4, 8])
+@pytest.mark.parametrize("R", [0, 1, 2, 4, 8, 16])
 def test_synthetic_full_table(gpu, oracle, name, R):
     g = GOLDEN["synthetic"][name]
     s1, s2 = synth_pair(g["seed"], g["n1"], g["n2"], g["alphabet_hi"])
@@ -37,6 +37,24 @@ def test_synthetic_full_table(gpu, oracle, name, R):
         assert np.array_equal(t, oracle.fill(s1, s2))
         assert p.score() == g["score"]
         assert np.array_equal(p.last_row(), t[-1]) and np.array_equal(p.last_col(), t[:, -1])
+
+
+@pytest.mark.parametrize("tile_blocks", [2, 3, 32])
+@pytest.mark.parametrize("R", [2, 8])
+def test_full_table_tiles_and_snapshots(gpu, oracle, monkeypatch, tile_blocks, R):
+    # packed full-table mode is two passes: pass 1 snapshots the warp state every `tile_blocks` blocks, pass 2 replays
+    # every tile independently.  Small tiles on a wide table exercise many snapshots, re-basing across tiles, the ragged
+    # last tile and the edge (predicated) blocks.
+    monkeypatch.setenv("NW_CUDA_TILE_BLOCKS", str(tile_blocks))
+    rng = np.random.default_rng(12)
+    s1 = rng.integers(1, 5, size=9000, dtype=np.int8)
+    s2 = np.concatenate([s1[:700], rng.integers(1, 5, size=333, dtype=np.int8)]).astype(np.int8)
+    with gpu.Plan(s1.size, s2.size, mode=gpu.NW_MODE_FULL, rows_per_lane=R) as p:
+        p.upload(s1, s2)
+        p.run()
+        assert np.array_equal(p.table_to_host(), oracle.fill(s1, s2))
+        p.run()                                   # a second epoch over the same buffers
+        assert np.array_equal(p.table_to_host(), oracle.fill(s1, s2))
 
 
 def test_2gb_full_table_golden(gpu, oracle):

@@ -1,3 +1,2 @@
-for r in 8 16; do for c in 6 7 8; do echo "R=$r ctas/sm=$c" >> gpurun_out/batch2.log; NW_CUDA_BATCH_R=$r NW_CUDA_BATCH_CTAS_PER_SM=$c python bench.py --workload batch --steps 3 --warmup 2 --batch-pairs 200000 >> gpurun_out/batch2.log 2>&1; done; done
-echo "default 1M pairs" >> gpurun_out/batch2.log
-python bench.py --workload batch --steps 3 --warmup 2 --batch-pairs 1000000 >> gpurun_out/batch2.log 2>&1
+python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "full or edge or random or column or tiles" 2>&1 | tail -8 > gpurun_out/pytest8.log
+for tb in 2 32; do for w in 8 4; do echo "warps2=$w tile_blocks=$tb" >> gpurun_out/full6.log; NW_CUDA_FULL_WARPS=$w NW_CUDA_TILE_BLOCKS=$tb python tools/full.py 8 2>&1 >> gpurun_out/full6.log; done; done
