@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(128) nw_batch16_kernel(const BatchParams p)
             uint32_t wnext = batch_col_operand<false>(s1, lane, ncols, lut);
             int pre = 0;
             if (s > 0 && lane < ncols) pre = scratch[lane];
+            uint32_t scar = __shfl_sync(FULL_MASK, h[R - 1], src_lane);
             for (int b = 0; b < nblocks; ++b) {
                 const int cb = b << 5;
 #pragma unroll
@@ -165,9 +166,9 @@ __global__ void __launch_bounds__(128) nw_batch16_kernel(const BatchParams p)
                 }
                 __syncwarp();
                 if (cb >= 64 && cb + 31 < ncols)
-                    sweep16<R, false, false>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols);
+                    sweep16<R, false, false>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols, scar);
                 else
-                    sweep16<R, true, false>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols);
+                    sweep16<R, true, false>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols, scar);
                 __syncwarp();
                 if (s + 1 < p.nstrips) {
                     const int oc = cb - 63 + lane;

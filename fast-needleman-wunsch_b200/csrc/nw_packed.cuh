@@ -34,7 +34,7 @@ template <int R, bool PRED, bool LOWLAT = true, bool TILE = false>
 __device__ __forceinline__ void sweep16(uint32_t (&h)[R], uint32_t& dprev, const uint32_t (&sel)[R],
                                         const uint32_t upsel, const int src_lane, const uint32_t* __restrict__ ringm,
                                         const uint32_t* __restrict__ sin, uint32_t* sout, const int lane, const int cb,
-                                        const int ncols, uint32_t* tile_lane = nullptr)
+                                        const int ncols, uint32_t& scar, uint32_t* tile_lane = nullptr)
 {
     const int i0 = cb - lane + (lane & 3);      // ring index (before & 127) of this lane's low column at k = 0; 4 | i0
     uint4 clo = *reinterpret_cast<const uint4*>(ringm + (i0 & 127));
@@ -55,7 +55,7 @@ __device__ __forceinline__ void sweep16(uint32_t (&h)[R], uint32_t& dprev, const
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             const int k = 4 * k4 + kk;
-            const uint32_t s = __shfl_sync(FULL_MASK, h[R - 1], src_lane);
+            const uint32_t s = scar;          // lane-1's last row, shuffled at the end of the previous step
             // off the chain: t[r] = max(G[i-1][j-1] + w, G[i][j-1]) and their prefix maxima, both halves at once
             uint32_t t[R];
             {
@@ -84,6 +84,7 @@ __device__ __forceinline__ void sweep16(uint32_t (&h)[R], uint32_t& dprev, const
                 {   // the last row first: it feeds the next step's shuffle
                     const uint32_t g = (R > 1) ? __vimax3_s16x2(t[R - 1], P[R > 1 ? R - 2 : 0], up0) : __vmaxs2(t[0], up0);
                     h[R - 1] = PRED ? ((g & mask) | (h[R - 1] & ~mask)) : g;
+                    scar = __shfl_sync(FULL_MASK, h[R - 1], src_lane);     // next step's input: start it as early as possible
                 }
 #pragma unroll
                 for (int r = 0; r + 1 < R; ++r) {
@@ -101,6 +102,7 @@ __device__ __forceinline__ void sweep16(uint32_t (&h)[R], uint32_t& dprev, const
                     if (r + 1 < R) h[r + 1] = PRED ? ((gb & mask) | (h[r + 1] & ~mask)) : gb;
                     g = gb;
                 }
+                scar = __shfl_sync(FULL_MASK, h[R - 1], src_lane);
             }
 #ifndef NW_DBG_NO_STS
             if (lane == 31) sout[k] = h[R - 1];
@@ -175,6 +177,7 @@ __device__ __forceinline__ void run_strip16(const StripParams& p, const int s, c
     if (s > 0 && lane < ncols) pre = ld_tagged_gpu(tin + lane + 1);
 
     const int nblocks = (ncols + 63 + 31) >> 5;          // the high half of lane 31 reaches column ncols-1 at t = ncols+62
+    uint32_t scar = __shfl_sync(FULL_MASK, h[R - 1], src_lane);
     for (int b = 0; b < nblocks; ++b) {
         const int cb = b << 5;
         // column operands of [cb, cb+32) into the four skewed ring copies; the ring then holds [cb-96, cb+32)
@@ -200,9 +203,9 @@ __device__ __forceinline__ void run_strip16(const StripParams& p, const int s, c
         }
         __syncwarp();
         if (cb >= 64 && cb + 31 < ncols)
-            sweep16<R, false>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols);
+            sweep16<R, false>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols, scar);
         else
-            sweep16<R, true>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols);
+            sweep16<R, true>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols, scar);
         __syncwarp();
         {
             const int oc = cb - 63 + lane;               // column finished by the high half of lane 31 at step k = lane
@@ -220,6 +223,7 @@ __device__ __forceinline__ void run_strip16(const StripParams& p, const int s, c
 #pragma unroll
                 for (int r = 0; r < R; ++r) h[r] -= Dp;
                 dprev -= Dp;
+                scar -= Dp;
                 base += D;
             }
         }
@@ -363,6 +367,7 @@ __global__ void __launch_bounds__(256) nw_full16_kernel(const StripParams p)
         if (s > 0 && (b0 << 5) + lane < ncols) pre = tin[(b0 << 5) + lane + 1].y;
         const long long tpitch = p.tpitch;
         int32_t* const table = p.table;
+        uint32_t scar = __shfl_sync(FULL_MASK, h[R - 1], src_lane);
         for (int b = b0; b < b1; ++b) {
             const int cb = b << 5;
 #pragma unroll
@@ -379,9 +384,9 @@ __global__ void __launch_bounds__(256) nw_full16_kernel(const StripParams p)
             __syncwarp();
             const bool interior = cb >= 64 && cb + 31 < ncols;
             if (interior)
-                sweep16<R, false, false, true>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols, tile_lane);
+                sweep16<R, false, false, true>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols, scar, tile_lane);
             else
-                sweep16<R, true, false, true>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols, tile_lane);
+                sweep16<R, true, false, true>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols, scar, tile_lane);
             __syncwarp();
             // write-out.  Slab row (L, r) holds, at position p, the packed cells of table column cb - L - 7 + p (low half;
             // the high half is 32 columns to the left and 32*R rows down): positions 0..7 are carried over from the
@@ -484,6 +489,7 @@ __global__ void __launch_bounds__(256) nw_full16_kernel(const StripParams p)
 #pragma unroll
                     for (int r = 0; r < R; ++r) h[r] -= Dp;
                     dprev -= Dp;
+                    scar -= Dp;
                     base += D;
                     // the carried-over columns in the tile are in the old base too; they may be smaller than D, so
                     // subtract half by half

@@ -1,5 +1,5 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -4 > gpurun_out/pytest9.log
-python bench.py --workload 2gb-full --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_2gbfull.json 2> gpurun_out/bench_2gbfull.err
-python bench.py --workload 2gb --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_2gb.json 2> gpurun_out/bench_2gb.err
-B=oracle/_ref/bdna; export NW_CUDA_TRACE=1
-for i in 1 2 3; do NW_CUDA_MODE=full fast-needleman-wunsch_b200/bin/cuda.e $B/2gb-1.bdna $B/2gb-2.bdna >> gpurun_out/driver4.log 2>&1; done
+python -m pytest tests -x -q -m gpu 2>&1 | tail -4 > gpurun_out/pytest10.log
+timeout 300 python tools/quick.py 2gb,mid,64gb 0 4 > gpurun_out/quick5.log 2>&1
+timeout 100 python tools/micro1.py >> gpurun_out/quick5.log 2>&1
+python bench.py --workload batch --steps 3 --warmup 2 --batch-pairs 200000 >> gpurun_out/quick5.log 2>&1
+python tools/full.py 8 2>&1 | head -1 >> gpurun_out/quick5.log
