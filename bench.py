@@ -383,6 +383,10 @@ def gpu_arm(args):
                 "ops_per_cell": ops_per_cell, "peak_source": f"measured here: nw_cuda_dpx_peak = {dpx_g:.0f} G lane-op/s "
                 f"per GPU at {dpx_mhz:.0f} MHz ({dpx_g * 1e3 / (148 * dpx_mhz):.1f} lanes/clk/SM)",
                 "peak_gcups": peak * 1e3 / ops_per_cell,
+                "note": "frac follows BASELINE.md section 4 (3 int32-pipe op per cell).  The kernel that ran packs two "
+                        "cells per DPX instruction (s16x2: 1.5 op per cell), so the pipe's own limit is twice peak_gcups; "
+                        "frac_s16x2 is the fraction of THAT limit." if info.get("packed", True) else "",
+                "frac_s16x2": achieved / peak / 2.0,
                 "hbm": {"achieved_gbs": hbm_bytes / (ms_step * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
                         "peak_source": "MEASURED_PEAKS.json" if peaks.get("hbm_gbs") else "absent",
                         "algorithmic_bytes_per_step": hbm_bytes},
@@ -462,7 +466,11 @@ def batch_arm(args, nw, torch, dist, world, rank, device):
                     "d2h_bytes_per_step": 4 * npairs},
             "gpu_launches": args.steps * world,
             "roofline": {"bound": "dpx-int32 pipe", "achieved": achieved, "peak": peak, "unit": "T int32 lane-op/s",
-                         "frac": achieved / peak, "traffic": None}}), flush=True)
+                         "frac": achieved / peak, "frac_s16x2": achieved / peak / 2.0, "ops_per_cell": 3.0,
+                         "note": "frac counts 3 int32-pipe op per cell (BASELINE.md section 4); it exceeds 1.0 because the "
+                                 "batch kernel packs two cells per DPX instruction (VIADDMNMX.S16x2, 1.5 op per cell); "
+                                 "frac_s16x2 is the fraction of the packed-instruction limit",
+                         "traffic": None}}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
