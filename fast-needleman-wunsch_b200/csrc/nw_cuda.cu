@@ -9,6 +9,7 @@
 #include "nw_kernels.cuh"
 #include "nw_packed.cuh"
 #include "nw_batch.cuh"
+#include "nw_packed2.cuh"
 
 #include <cooperative_groups.h>
 #include <algorithm>
@@ -82,6 +83,17 @@ StripKernel strip16_kernel(int regs)
     case 2: return nw::nw_strip16_kernel<2>;
     case 4: return nw::nw_strip16_kernel<4>;
     case 8: return nw::nw_strip16_kernel<8>;
+    default: return nullptr;
+    }
+}
+
+StripKernel strip16k2_kernel(int regs)
+{
+    switch (regs) {
+    case 1: return nw::nw_strip16k2_kernel<1>;
+    case 2: return nw::nw_strip16k2_kernel<2>;
+    case 4: return nw::nw_strip16k2_kernel<4>;
+    case 8: return nw::nw_strip16k2_kernel<8>;
     default: return nullptr;
     }
 }
@@ -161,6 +173,7 @@ struct nw_plan {
     int R_req = 0, warps_req = 0, ctas_req = 0;      // what the caller asked for (0 = automatic)
     int warps = 8, ctas = 0, nstrips = 0, pad_top = 0;
     bool packed = false;  // nw_packed.cuh kernel (boundary mode, at most four distinct byte values)
+    bool k2 = false;      // nw_packed2.cuh: two columns per step (boundary mode, wide tables)
     bool generic = false, uploaded = false;
     size_t rsel_words = 0, brow_words = 0;
     int epoch = 0;
@@ -385,7 +398,18 @@ static int plan_pick_kernel(nw_plan* p)
         CK(cudaMemsetAsync(p->d_brow, 0, sizeof(int2) * brow_words, p->stream));    // tags must not match any epoch
         p->brow_words = brow_words;
     }
-    if (p->packed) {
+    // Two columns per step (nw_packed2.cuh) cut the per-column time from ~58 to ~48 cycles but a strip then starts
+    // ~390 columns after its predecessor instead of ~137 (measured on B200, profiles/r01_k2_sweep.log): break-even at
+    // ncols ~ 1100 x strips, so only very wide, short tables take it.  NW_CUDA_K2=0/1 forces the choice.
+    {
+        const int k2env = env_int("NW_CUDA_K2", -1);
+        p->k2 = p->packed && p->mode == NW_MODE_BOUNDARY &&
+                (k2env >= 0 ? k2env != 0 : (long long)p->ncols >= 1200LL * std::max(1, p->nstrips));
+    }
+    if (p->packed && p->k2) {
+        p->kernel = strip16k2_kernel(R / 2);
+        p->smem = sizeof(uint32_t) * nw::SMEM16K2_WORDS_PER_WARP * (size_t)p->warps;
+    } else if (p->packed) {
         p->kernel = strip16_kernel(R / 2);
         p->smem = sizeof(uint32_t) * nw::SMEM16_WORDS_PER_WARP * (size_t)p->warps;
     } else {

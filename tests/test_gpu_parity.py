@@ -88,11 +88,14 @@ def test_boundaries_match_golden_hashes(gpu, oracle, name, kernel_kind):
     assert oracle.fnv(row) == g["fnv_lastrow"] and oracle.fnv(col) == g["fnv_lastcol"] and sc == g["score"]
 
 
-@pytest.fixture(params=["packed16", "int32"])
+@pytest.fixture(params=["packed16", "packed16k2", "int32"])
 def kernel_kind(request, monkeypatch):
-    """Boundary mode has two kernels: packed s16x2 (nw_packed.cuh, default) and 32-bit (nw_kernels.cuh)."""
+    """Boundary mode has three kernels: packed s16x2 with one column per step (nw_packed.cuh), with two columns per step
+    (nw_packed2.cuh; chosen automatically for wide tables) and 32-bit (nw_kernels.cuh)."""
     if request.param == "int32":
         monkeypatch.setenv("NW_CUDA_NO_PACKED", "1")
+    else:
+        monkeypatch.setenv("NW_CUDA_K2", "1" if request.param == "packed16k2" else "0")
     return request.param
 
 
@@ -136,8 +139,10 @@ def test_many_random_shapes(gpu, oracle, kernel_kind):
         assert np.array_equal(row, t[-1]) and np.array_equal(col, t[:, -1]) and sc == t[-1, -1], (n1, n2, hi)
 
 
+@pytest.mark.parametrize("k2", ["0", "1"])
 @pytest.mark.parametrize("R", [0, 2, 4, 8, 16])
-def test_boundaries_long_rows_rebase(gpu, oracle, R):
+def test_boundaries_long_rows_rebase(gpu, oracle, R, k2, monkeypatch):
+    monkeypatch.setenv("NW_CUDA_K2", k2)
     # wide tables make the packed kernel re-base its 16-bit lanes many times; identical prefixes make G grow fastest
     rng = np.random.default_rng(9)
     s1 = rng.integers(1, 5, size=40000, dtype=np.int8)

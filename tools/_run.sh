@@ -1,5 +1,2 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -4 > gpurun_out/pytest10.log
-timeout 300 python tools/quick.py 2gb,mid,64gb 0 4 > gpurun_out/quick5.log 2>&1
-timeout 100 python tools/micro1.py >> gpurun_out/quick5.log 2>&1
-python bench.py --workload batch --steps 3 --warmup 2 --batch-pairs 200000 >> gpurun_out/quick5.log 2>&1
-python tools/full.py 8 2>&1 | head -1 >> gpurun_out/quick5.log
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -6 > gpurun_out/pytest12.log
+for k in 0 1; do echo "K2=$k" >> gpurun_out/quick8.log; NW_CUDA_K2=$k timeout 300 python tools/quick.py 2gb,mid,big,64gb 0,4,8,16 4 >> gpurun_out/quick8.log 2>&1; NW_CUDA_K2=$k timeout 100 python tools/micro1.py >> gpurun_out/quick8.log 2>&1; done
