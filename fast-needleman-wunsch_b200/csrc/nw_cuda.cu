@@ -930,6 +930,38 @@ extern "C" int nw_plan_table_device(nw_plan* p, int32_t** d_table, int64_t* pitc
     return NW_OK;
 }
 
+extern "C" int nw_plan_traceback(nw_plan* p, int8_t* a1, int8_t* a2, int32_t* len)
+{
+    if (!p || !a1 || !a2 || !len) return fail(NW_ERR_ARG, "bad argument");
+    if (p->mode != NW_MODE_FULL) return fail(NW_ERR_STATE, "traceback needs a full-table plan");
+    if (p->nparts != 1) return fail(NW_ERR_UNSUPPORTED, "traceback needs the whole table on one device");
+    if (p->epoch == 0) return fail(NW_ERR_STATE, "no fill has been run");
+    CK(cudaSetDevice(p->device));
+    const size_t cap = (size_t)p->n1 + (size_t)p->n2 + 1;
+    uint8_t* d_out = nullptr;
+    int* d_len = nullptr;
+    CK(cudaMalloc(&d_out, 2 * cap));
+    CK(cudaMalloc(&d_len, sizeof(int)));
+    nw::nw_traceback_kernel<<<1, 256, 0, p->stream>>>(p->d_table, p->tpitch, p->d_s1, p->d_s2, p->n1, p->n2, d_out,
+                                                      d_out + cap, d_len);
+    cudaError_t e = cudaGetLastError();
+    int n = 0;
+    std::vector<uint8_t> r1(cap), r2(cap);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&n, d_len, sizeof(int), cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(r1.data(), d_out, cap, cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(r2.data(), d_out + cap, cap, cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    cudaFree(d_out);
+    cudaFree(d_len);
+    if (e != cudaSuccess) return fail(NW_ERR_CUDA, "traceback: %s", cudaGetErrorString(e));
+    for (int k = 0; k < n; ++k) {            // the kernel emits the path backwards
+        a1[k] = (int8_t)r1[(size_t)n - 1 - k];
+        a2[k] = (int8_t)r2[(size_t)n - 1 - k];
+    }
+    *len = n;
+    return NW_OK;
+}
+
 extern "C" int nw_plan_strip_info(nw_plan* p, int* nstrips, int* strip_rows, int* rows_per_lane, int* warps, int* ctas)
 {
     if (!p) return fail(NW_ERR_ARG, "plan is NULL");

@@ -408,6 +408,70 @@ __global__ void nw_presence_kernel64(const uint8_t* s, long long n, uint32_t* bi
     if (threadIdx.x < 8 && bm[threadIdx.x]) atomicOr(&bitmap[threadIdx.x], bm[threadIdx.x]);
 }
 
+// ---- traceback on a materialised table ----------------------------------------------------------------
+// One CTA walks back from H[n2][n1] to H[0][0].  The table lives in HBM, so a naive walk would pay one dependent global
+// load per step; instead the CTA stages a 64 x 64 window ending at the current cell in shared memory (coalesced row
+// segments), thread 0 walks inside it until it leaves, and the window is re-staged.  Rule per cell (the reference
+// defines none; this is the oracle's): diagonal if H[i][j] == H[i-1][j-1] + (s1[j-1]==s2[i-1]), else up if
+// H[i][j] == H[i-1][j] - 1, else left.  Output: the two gapped sequences REVERSED (gap = 0, README.md:8), and the length.
+constexpr int TB_W = 64;
+__global__ void __launch_bounds__(256) nw_traceback_kernel(const int32_t* __restrict__ table, long long tpitch,
+                                                           const uint8_t* __restrict__ s1, const uint8_t* __restrict__ s2,
+                                                           int n1, int n2, uint8_t* out1, uint8_t* out2, int* out_len)
+{
+    __shared__ int win[TB_W][TB_W + 1];
+    __shared__ uint8_t c1[TB_W], c2[TB_W];
+    __shared__ int pos[3];                 // i, j, emitted
+    if (threadIdx.x == 0) { pos[0] = n2; pos[1] = n1; pos[2] = 0; }
+    __syncthreads();
+    for (;;) {
+        const int i = pos[0], j = pos[1];
+        if (i == 0 && j == 0) break;
+        const int wi0 = max(i - (TB_W - 1), 0), wj0 = max(j - (TB_W - 1), 0);     // window = rows wi0..i, cols wj0..j
+        const int nr = i - wi0 + 1, nc = j - wj0 + 1;
+        for (int x = threadIdx.x; x < nr * TB_W; x += blockDim.x) {
+            const int r = x / TB_W, c = x - r * TB_W;
+            if (c < nc) win[r][c] = table[(long long)(wi0 + r) * tpitch + wj0 + c];
+        }
+        // s1[jj-1] for table columns jj = wj0+1..j  ->  c1[jj - wj0];  s2[ii-1] for rows ii = wi0+1..i -> c2[ii - wi0]
+        if (threadIdx.x < TB_W) {
+            const int c = threadIdx.x;
+            if (c >= 1 && c < nc) c1[c] = s1[wj0 + c - 1];
+            if (c >= 1 && c < nr) c2[c] = s2[wi0 + c - 1];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int a = nr - 1, b = nc - 1, k = pos[2];            // window coordinates of (i, j)
+            // walk while the three neighbours are inside the window, or the move is forced by a table edge
+            for (;;) {
+                const int gi = wi0 + a, gj = wj0 + b;
+                if (gi == 0 && gj == 0) break;
+                int move;                                      // 0 diag, 1 up, 2 left
+                if (gi == 0) move = 2;
+                else if (gj == 0) move = 1;
+                else {
+                    if (a == 0 || b == 0) break;               // neighbours outside: re-stage the window
+                    const int h = win[a][b];
+                    if (h == win[a - 1][b - 1] + (c1[b] == c2[a] ? 1 : 0)) move = 0;
+                    else if (h == win[a - 1][b] - 1) move = 1;
+                    else move = 2;
+                }
+                if (move == 2 && gi == 0 && b == 0) break;     // need the previous window for the sequence byte
+                if (move == 1 && gj == 0 && a == 0) break;
+                if (move == 0) { out1[k] = c1[b]; out2[k] = c2[a]; --a; --b; }
+                else if (move == 1) { out1[k] = 0; out2[k] = c2[a]; --a; }
+                else { out1[k] = c1[b]; out2[k] = 0; --b; }
+                ++k;
+            }
+            pos[0] = wi0 + a;
+            pos[1] = wj0 + b;
+            pos[2] = k;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out_len = pos[2];
+}
+
 // integer / DPX pipe rate: 8 independent VIADDMNMX chains per thread (roofline denominator)
 constexpr int DPX_PEAK_OPS_PER_ITER = 8;
 __global__ void nw_dpx_peak_kernel(int* out, unsigned long long* clk, int iters, int seed)

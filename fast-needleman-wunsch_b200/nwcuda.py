@@ -21,7 +21,7 @@ EXPORTS = [
     "nw_plan_create", "nw_plan_destroy", "nw_plan_upload", "nw_plan_upload_device", "nw_plan_connect",
     "nw_plan_export_mailbox", "nw_plan_import_mailbox", "nw_plan_run", "nw_plan_sync", "nw_plan_time",
     "nw_plan_timer_start", "nw_plan_timer_stop", "nw_plan_last_ms", "nw_plan_launches_per_run", "nw_plan_score", "nw_plan_last_row", "nw_plan_last_col",
-    "nw_plan_table_to_host", "nw_plan_table_device", "nw_plan_strip_info", "nw_plan_strip_row",
+    "nw_plan_table_to_host", "nw_plan_table_device", "nw_plan_traceback", "nw_plan_strip_info", "nw_plan_strip_row",
     "nw_batch_create", "nw_batch_destroy", "nw_batch_upload", "nw_batch_upload_device", "nw_batch_run",
     "nw_batch_sync", "nw_batch_time", "nw_batch_scores", "nw_cuda_dpx_peak",
 ]
@@ -65,6 +65,7 @@ def lib():
             "nw_plan_last_ms": [vp, C.POINTER(C.c_float)], "nw_plan_launches_per_run": [vp, ip],
             "nw_plan_score": [vp, vp], "nw_plan_last_row": [vp, vp], "nw_plan_last_col": [vp, vp],
             "nw_plan_table_to_host": [vp, vp], "nw_plan_table_device": [vp, C.POINTER(vp), C.POINTER(i64)],
+            "nw_plan_traceback": [vp, vp, vp, ip],
             "nw_plan_strip_info": [vp, ip, ip, ip, ip, ip], "nw_plan_strip_row": [vp, C.c_int, vp],
             "nw_batch_create": [C.POINTER(vp), C.c_int, i64, i32, i32], "nw_batch_destroy": [vp],
             "nw_batch_upload": [vp, vp, vp], "nw_batch_upload_device": [vp, vp, vp], "nw_batch_run": [vp],
@@ -103,6 +104,11 @@ def readSequence(fileName):
         return np.fromfile(fileName, dtype=np.int8)
     except (FileNotFoundError, OSError) as e:
         raise FileNotFoundError(fileName) from e
+
+
+def printSequence(a):
+    """The reference's printer as a string: 0..4 -> "-ATGC" (src/common/helper.cpp:27-34)."""
+    return "".join("-ATGC"[int(x)] for x in a)
 
 
 def device_count():
@@ -277,6 +283,14 @@ class Plan:
         ptr, pitch = C.c_void_p(), C.c_int64()
         _ck(lib().nw_plan_table_device(self._h, C.byref(ptr), C.byref(pitch)))
         return ptr.value, pitch.value
+
+    def traceback(self):
+        """(a1, a2): the gapped s1 and s2 of the optimal alignment the table encodes, gap = 0 (README.md:8)."""
+        cap = self.n1 + self.n2 + 1
+        a1, a2 = np.empty(cap, dtype=np.int8), np.empty(cap, dtype=np.int8)
+        n = C.c_int()
+        _ck(lib().nw_plan_traceback(self._h, a1.ctypes.data, a2.ctypes.data, C.byref(n)))
+        return a1[:n.value].copy(), a2[:n.value].copy()
 
     def strip_info(self):
         v = [C.c_int() for _ in range(5)]

@@ -61,6 +61,8 @@ class Oracle:
         L.nw_oracle_strip_partition.restype = None
         L.nw_oracle_strip.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp]
         L.nw_oracle_strip.restype = i32
+        L.nw_oracle_traceback.argtypes = [vp, i32, vp, i32, vp, vp]
+        L.nw_oracle_traceback.restype = i32
         L.nw_oracle_fnv1a64.argtypes = [vp, i64]
         L.nw_oracle_fnv1a64.restype = C.c_uint64
         L.nw_oracle_fnv1a64_col.argtypes = [vp, i64, i64]
@@ -104,6 +106,12 @@ class Oracle:
         last = self.L.nw_oracle_strip(self._p(s1), s1.size, self._p(s2), s2.size, P, p,
                                       halo.ctypes.data if halo is not None else None, right.ctypes.data)
         return right, int(last)
+
+    def traceback(self, s1, s2):
+        a1 = np.empty(s1.size + s2.size + 1, dtype=np.int8)
+        a2 = np.empty(s1.size + s2.size + 1, dtype=np.int8)
+        n = self.L.nw_oracle_traceback(self._p(s1), s1.size, self._p(s2), s2.size, a1.ctypes.data, a2.ctypes.data)
+        return a1[:n].copy(), a2[:n].copy()
 
     def fnv(self, a):
         a = np.ascontiguousarray(a)

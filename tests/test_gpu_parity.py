@@ -390,3 +390,45 @@ def test_batch_more_shapes(gpu, oracle, shape, kernel_kind):
     S2 = rng.integers(1, 5, size=(npairs, len2), dtype=np.int8)
     S2[0, :min(len1, len2)] = S1[0, :min(len1, len2)]      # one near-identical pair: the largest scores
     assert np.array_equal(gpu.batch_scores(S1, S2), oracle.batch_scores(S1, S2))
+
+
+# ---- traceback on the materialised table ---------------------------------------------------------------
+@pytest.mark.parametrize("name", ["small", "t", "debug", "smid"])
+def test_traceback_fixtures(gpu, oracle, name):
+    s1, s2 = load_pair(name)
+    with gpu.Plan(s1.size, s2.size, mode=gpu.NW_MODE_FULL) as p:
+        p.upload(s1, s2)
+        p.run()
+        a1, a2 = p.traceback()
+    b1, b2 = oracle.traceback(s1, s2)
+    assert np.array_equal(a1, b1) and np.array_equal(a2, b2)
+    gaps = int((a1 == 0).sum() + (a2 == 0).sum())
+    assert int(((a1 == a2) & (a1 != 0)).sum()) - gaps == GOLDEN["fixtures"][name]["score"]
+    assert set(gpu.printSequence(a1[:50])) <= set("-ATGC")
+
+
+@pytest.mark.parametrize("shape", [(0, 0), (0, 9), (9, 0), (1, 1), (63, 64), (64, 63), (65, 129), (700, 90), (90, 700),
+                                   (2000, 2100)])
+def test_traceback_shapes(gpu, oracle, shape, kernel_kind):
+    n1, n2 = shape
+    s1, s2 = synth_pair(900 + n1 + 3 * n2, n1, n2, 5)
+    with gpu.Plan(n1, n2, mode=gpu.NW_MODE_FULL) as p:
+        p.upload(s1, s2)
+        p.run()
+        a1, a2 = p.traceback()
+    b1, b2 = oracle.traceback(s1, s2)
+    assert np.array_equal(a1, b1) and np.array_equal(a2, b2)
+
+
+def test_traceback_2gb_properties(gpu):
+    # full BASELINE size: the alignment reproduces both sequences and its column score is the golden score
+    s1, s2 = load_pair("2gb")
+    with gpu.Plan(s1.size, s2.size, mode=gpu.NW_MODE_FULL) as p:
+        p.upload(s1, s2)
+        p.run()
+        a1, a2 = p.traceback()
+        with pytest.raises(gpu.NwCudaError):
+            gpu.Plan(10, 10).traceback()
+    assert np.array_equal(a1[a1 != 0], s1) and np.array_equal(a2[a2 != 0], s2)
+    gaps = int((a1 == 0).sum() + (a2 == 0).sum())
+    assert int(((a1 == a2) & (a1 != 0)).sum()) - gaps == GOLDEN["fixtures"]["2gb"]["score"]

@@ -95,3 +95,29 @@ def test_batch(oracle):
     sc = oracle.batch_scores(S1, S2)
     for p in (0, 17, 49):
         assert sc[p] == oracle.fill(S1[p], S2[p])[-1, -1]
+
+
+def _check_alignment(s1, s2, a1, a2, score):
+    assert a1.size == a2.size
+    assert not ((a1 == 0) & (a2 == 0)).any()                       # never gap against gap
+    assert np.array_equal(a1[a1 != 0], s1) and np.array_equal(a2[a2 != 0], s2)
+    gaps = int((a1 == 0).sum() + (a2 == 0).sum())
+    matches = int(((a1 == a2) & (a1 != 0)).sum())
+    assert matches - gaps == score                                 # MATCH +1, MISMATCH 0, GAP -1
+
+
+@pytest.mark.parametrize("shape", [(0, 0), (0, 4), (4, 0), (1, 1), (6, 10), (300, 280), (1000, 40)])
+def test_traceback_is_an_optimal_alignment(oracle, shape):
+    n1, n2 = shape
+    s1, s2 = synth_pair(5 + n1 + n2, n1, n2, 5)
+    a1, a2 = oracle.traceback(s1, s2)
+    _check_alignment(s1, s2, a1, a2, oracle.score(s1, s2))
+
+
+def test_traceback_small_fixture_literal(oracle):
+    # the `small` pair: score 2
+    s1 = np.array([1, 3, 1, 1, 3, 4], dtype=np.int8)
+    s2 = np.array([2, 1, 1, 3, 1, 1, 1, 1, 3, 4], dtype=np.int8)
+    a1, a2 = oracle.traceback(s1, s2)
+    _check_alignment(s1, s2, a1, a2, 2)
+    assert a1.size == 10
