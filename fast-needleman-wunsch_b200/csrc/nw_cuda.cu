@@ -20,6 +20,7 @@
 #include <mutex>
 #include <thread>
 #include <new>
+#include <string>
 #include <vector>
 
 namespace {
@@ -202,6 +203,14 @@ struct nw_plan {
     uint32_t* d_snap = nullptr;
     size_t snap_words = 0, smem2 = 0;
     int tile_blocks = 32, ntiles = 1, ctas2 = 0, warps2 = 5;
+    // streamed table delivery (one-shot calls with a HOST table): the device never holds the whole table; pass 2 runs
+    // band by band into a two-band ring while the previous band is on its way to the host
+    bool want_streamed = false, streamed = false;
+    int band_strips = 0;
+    size_t table_elems = 0;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t band_ev[2] = {nullptr, nullptr};
+    nw::StripParams last_sp;         // parameters of the most recent fill (pass 2 of a streamed delivery reuses them)
 };
 
 static int ensure_device(int device)
@@ -318,6 +327,9 @@ extern "C" int nw_plan_destroy(nw_plan* p)
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->ev2) cudaEventDestroy(p->ev2);
     if (p->ev3) cudaEventDestroy(p->ev3);
+    for (int i = 0; i < 2; ++i)
+        if (p->band_ev[i]) cudaEventDestroy(p->band_ev[i]);
+    if (p->stream2) cudaStreamDestroy(p->stream2);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
     return NW_OK;
@@ -358,8 +370,7 @@ static int plan_alloc(nw_plan* p, const nw_tuning* tuning)
     p->rcol_target = p->d_rcol_local;
     if (p->mode == NW_MODE_FULL) {
         p->tpitch = ((long long)nc + 1 + 7) & ~7LL;      // rows start on a 32-byte sector: the table stores need it
-        CK(cudaMalloc(&p->d_table, sizeof(int32_t) * (size_t)p->tpitch * ((size_t)n2 + 1)));
-        CK(cudaMalloc(&p->d_dump, sizeof(int32_t) * (size_t)p->tpitch));
+        CK(cudaMalloc(&p->d_dump, sizeof(int32_t) * (size_t)p->tpitch));      // the table itself: plan_pick_kernel
     }
     CK(cudaMalloc(&p->d_last_row, sizeof(int32_t) * ((size_t)nc + 1)));
     CK(cudaMalloc(&p->d_last_col, sizeof(int32_t) * ((size_t)n2 + 1)));
@@ -441,6 +452,30 @@ static int plan_pick_kernel(nw_plan* p)
         p->ctas2 = (int)std::max<long long>(1, std::min<long long>((ntasks + p->warps2 - 1) / p->warps2,
                                                                      (long long)d.sm_count * per_sm2));
     }
+    if (p->mode == NW_MODE_FULL) {
+        // whole table, or (streamed delivery, packed kernels only) a ring of two bands of ~256 MB
+        p->streamed = p->want_streamed && p->kernel2 != nullptr && p->nparts == 1 && p->ncols > 0 && p->n2 > 0 &&
+                      !env_int("NW_CUDA_NO_STREAMED", 0);
+        size_t elems = (size_t)p->tpitch * ((size_t)p->n2 + 1);
+        if (p->streamed) {
+            const size_t band_bytes = (size_t)std::max(16, env_int("NW_CUDA_BAND_MB", 256)) << 20;
+            const size_t strip_bytes = sizeof(int32_t) * (size_t)p->tpitch * 32u * (size_t)R;
+            p->band_strips = (int)std::max<size_t>(1, band_bytes / strip_bytes);
+            if (p->band_strips >= p->nstrips) p->streamed = false;          // one band would hold everything anyway
+            else elems = 2 * (size_t)p->tpitch * ((size_t)p->band_strips * 32u * (size_t)R + 1);
+        }
+        if (elems > p->table_elems) {
+            if (p->d_table) CK(cudaFree(p->d_table));
+            p->d_table = nullptr;
+            CK(cudaMalloc(&p->d_table, sizeof(int32_t) * elems));
+            p->table_elems = elems;
+        }
+        if (p->streamed && !p->stream2) {
+            CK(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&p->band_ev[0], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&p->band_ev[1], cudaEventDisableTiming));
+        }
+    }
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p->kernel, p->warps * 32, p->smem));
     if (per_sm < 1) return fail(NW_ERR_CUDA, "strip kernel does not fit on an SM (warps=%d)", p->warps);
@@ -457,8 +492,17 @@ static int plan_pick_kernel(nw_plan* p)
     return NW_OK;
 }
 
+static int plan_create_internal(nw_plan** out, int device, int32_t n1, int32_t n2, int mode, int part, int nparts,
+                                const nw_tuning* tuning, bool want_streamed);
+
 extern "C" int nw_plan_create(nw_plan** out, int device, int32_t n1, int32_t n2, int mode, int part, int nparts,
                               const nw_tuning* tuning)
+{
+    return plan_create_internal(out, device, n1, n2, mode, part, nparts, tuning, false);
+}
+
+static int plan_create_internal(nw_plan** out, int device, int32_t n1, int32_t n2, int mode, int part, int nparts,
+                                const nw_tuning* tuning, bool want_streamed)
 {
     if (!out) return fail(NW_ERR_ARG, "out is NULL");
     *out = nullptr;
@@ -477,6 +521,7 @@ extern "C" int nw_plan_create(nw_plan** out, int device, int32_t n1, int32_t n2,
     p->mode = mode;
     p->part = part;
     p->nparts = nparts;
+    p->want_streamed = want_streamed;
     partition(n1, nparts, part, &p->jstart, &p->ncols);
     rc = plan_alloc(p, tuning);
     if (rc == NW_OK) rc = plan_pick_kernel(p);        // provisional (assumes the four-letter alphabet) so that
@@ -612,7 +657,7 @@ static int plan_enqueue(nw_plan* p)
     const int2* halo = (p->part > 0) ? p->d_mailbox + (long long)par * p->mpitch : nullptr;
     int2* rcol = p->rcol_target + (long long)par * p->mpitch;
     const bool have_cells = p->ncols > 0 && p->n2 > 0;
-    if (p->mode == NW_MODE_FULL) {
+    if (p->mode == NW_MODE_FULL && !p->streamed) {
         nw::nw_table_row0_kernel<<<64, 256, 0, p->stream>>>(p->d_table, p->ncols, p->jstart);
         CK(cudaGetLastError());
         if (!have_cells && p->n2 > 0) {   // no interior column: the table is just the boundary column
@@ -644,9 +689,12 @@ static int plan_enqueue(nw_plan* p)
         sp.snap = p->kernel2 ? p->d_snap : nullptr;
         sp.tile_blocks = p->tile_blocks;
         sp.ntiles = p->ntiles;
+        sp.s_begin = 0;
+        sp.s_count = p->nstrips;
         void* args[] = {&sp};
         CK(cudaLaunchCooperativeKernel((const void*)p->kernel, dim3(p->ctas), dim3(p->warps * 32), args, p->smem, p->stream));
-        if (p->kernel2 && !env_int("NW_CUDA_DBG_SKIP_PASS2", 0)) {           // pass 2: every tile of every strip at once, table stores as 128-byte row segments
+        p->last_sp = sp;
+        if (p->kernel2 && !p->streamed && !env_int("NW_CUDA_DBG_SKIP_PASS2", 0)) {           // pass 2: every tile of every strip at once, table stores as 128-byte row segments
             sp.ack_in = nullptr;
             p->kernel2<<<p->ctas2, p->warps2 * 32, p->smem2, p->stream>>>(sp);
             CK(cudaGetLastError());
@@ -780,8 +828,8 @@ struct Staging {
     size_t bytes = 0;
     int device = -1;
 };
-Staging g_stage;
-std::mutex g_stage_mu;
+Staging g_stages[64];              // one pair of pinned buffers per device: parts of a pipeline deliver concurrently
+std::mutex g_stage_mus[64];
 
 void parallel_memcpy(char* dst, const char* src, size_t n, int nthreads)
 {
@@ -811,8 +859,9 @@ bool host_pointer_is_pinned(const void* p)
 }
 }  // namespace
 
-static int ensure_staging(int device)       // caller holds g_stage_mu
+static int ensure_staging(int device)       // caller holds g_stage_mus[device]
 {
+    Staging& g_stage = g_stages[device];
     const size_t chunk = (size_t)std::max(1, env_int("NW_CUDA_STAGE_MB", 32)) << 20;
     if (g_stage.bytes == chunk && g_stage.device == device) return NW_OK;
     CK(cudaSetDevice(device));
@@ -833,13 +882,17 @@ static int ensure_staging(int device)       // caller holds g_stage_mu
 }
 
 // rows x width bytes from device (pitch dpitch) to host (pitch hpitch), host pageable
-static int staged_d2h_2d(nw_plan* p, char* dst, size_t hpitch, const char* src, size_t dpitch, size_t width, size_t rows)
+static int staged_d2h_2d(nw_plan* p, char* dst, size_t hpitch, const char* src, size_t dpitch, size_t width, size_t rows,
+                         cudaStream_t cs = nullptr)
 {
-    std::lock_guard<std::mutex> lk(g_stage_mu);
+    if (cs == nullptr) cs = p->stream;
+    std::lock_guard<std::mutex> lk(g_stage_mus[p->device]);
     int rc0 = ensure_staging(p->device);
     if (rc0) return rc0;
+    Staging& g_stage = g_stages[p->device];
     const size_t chunk = g_stage.bytes;
-    const int nthreads = std::max(1, std::min(env_int("NW_CUDA_COPY_THREADS", 12), (int)std::thread::hardware_concurrency()));
+    const int nthreads = std::max(1, std::min(env_int("NW_CUDA_COPY_THREADS", 12), (int)std::thread::hardware_concurrency()) /
+                                      std::max(1, p->nparts > 1 ? std::min(p->nparts, 4) : 1));
     const bool flat = (width == hpitch && width == dpitch);
     // unit of work: a run of whole rows (or a byte range when the table is contiguous on both sides)
     const size_t total = flat ? width * rows : rows;
@@ -851,10 +904,10 @@ static int staged_d2h_2d(nw_plan* p, char* dst, size_t hpitch, const char* src, 
     while (done_copy < total) {
         if (done_issue < total && !pending[slot]) {
             const size_t n = std::min(step, total - done_issue);
-            if (flat) CK(cudaMemcpyAsync(g_stage.buf[slot], src + done_issue, n, cudaMemcpyDeviceToHost, p->stream));
+            if (flat) CK(cudaMemcpyAsync(g_stage.buf[slot], src + done_issue, n, cudaMemcpyDeviceToHost, cs));
             else CK(cudaMemcpy2DAsync(g_stage.buf[slot], width, src + done_issue * dpitch, dpitch, width, n,
-                                      cudaMemcpyDeviceToHost, p->stream));
-            CK(cudaEventRecord(g_stage.ev[slot], p->stream));
+                                      cudaMemcpyDeviceToHost, cs));
+            CK(cudaEventRecord(g_stage.ev[slot], cs));
             pend_off[slot] = done_issue;
             pend_n[slot] = n;
             pending[slot] = true;
@@ -889,12 +942,53 @@ static int staged_d2h_2d(nw_plan* p, char* dst, size_t hpitch, const char* src, 
     return NW_OK;
 }
 
+// Streamed delivery: pass 2 of band k+1 (kernel, stream) overlaps the device->host copy of band k (stream2 + host threads).
+static int plan_stream_table_to_host(nw_plan* p, int32_t* table)
+{
+    CK(cudaSetDevice(p->device));
+    const int SH = 32 * p->R;
+    const size_t band_rows = (size_t)p->band_strips * SH + 1;                 // + table row 0 in band 0
+    const size_t band_elems = (size_t)p->tpitch * band_rows;
+    const size_t host_pitch = sizeof(int32_t) * ((size_t)p->n1 + 1), dpitch = sizeof(int32_t) * (size_t)p->tpitch;
+    const int nbands = (p->nstrips + p->band_strips - 1) / p->band_strips;
+    auto first_row = [&](int k) { return k == 0 ? 0LL : (long long)k * p->band_strips * SH - p->pad_top + 1; };
+    auto last_row = [&](int k) { return std::min<long long>(p->n2, (long long)(k + 1) * p->band_strips * SH - p->pad_top); };
+    auto launch = [&](int k) -> int {
+        nw::StripParams sp = p->last_sp;
+        int32_t* buf = p->d_table + (size_t)(k & 1) * band_elems;
+        sp.table = buf - first_row(k) * p->tpitch;                            // the kernel indexes by table row
+        sp.s_begin = k * p->band_strips;
+        sp.s_count = std::min(p->band_strips, p->nstrips - sp.s_begin);
+        sp.ack_in = nullptr;
+        if (k == 0) nw::nw_table_row0_kernel<<<64, 256, 0, p->stream>>>(buf, p->ncols, p->jstart);
+        const long long ntasks = (long long)sp.s_count * p->ntiles;
+        const int ctas = (int)std::max<long long>(1, std::min<long long>((ntasks + p->warps2 - 1) / p->warps2, p->ctas2));
+        p->kernel2<<<ctas, p->warps2 * 32, p->smem2, p->stream>>>(sp);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(p->band_ev[k & 1], p->stream));
+        return NW_OK;
+    };
+    int rc = launch(0);
+    for (int k = 0; k < nbands && rc == NW_OK; ++k) {
+        // band k+1 goes into the other half of the ring, whose previous content (band k-1) has already been delivered
+        if (k + 1 < nbands) rc = launch(k + 1);
+        if (rc != NW_OK) break;
+        CK(cudaStreamWaitEvent(p->stream2, p->band_ev[k & 1], 0));
+        const long long r0 = first_row(k), r1 = last_row(k);
+        rc = staged_d2h_2d(p, (char*)table + (size_t)r0 * host_pitch, host_pitch,
+                           (const char*)(p->d_table + (size_t)(k & 1) * band_elems), dpitch, host_pitch,
+                           (size_t)(r1 - r0 + 1), p->stream2);
+    }
+    return rc;
+}
+
 extern "C" int nw_plan_table_to_host(nw_plan* p, int32_t* table)
 {
     if (!p || !table) return fail(NW_ERR_ARG, "bad argument");
     if (p->mode != NW_MODE_FULL) return fail(NW_ERR_STATE, "plan is not in full-table mode");
     if (p->epoch == 0) return fail(NW_ERR_STATE, "no fill has been run");
     CK(cudaSetDevice(p->device));
+    if (p->streamed) return plan_stream_table_to_host(p, table);
     const size_t host_pitch = sizeof(int32_t) * ((size_t)p->n1 + 1);
     // parts > 0 own their halo column too, but it is the left neighbour's last column: copy interior columns only
     const int skip = (p->part > 0) ? 1 : 0;
@@ -925,6 +1019,7 @@ extern "C" int nw_plan_table_device(nw_plan* p, int32_t** d_table, int64_t* pitc
 {
     if (!p || !d_table || !pitch) return fail(NW_ERR_ARG, "bad argument");
     if (p->mode != NW_MODE_FULL) return fail(NW_ERR_STATE, "plan is not in full-table mode");
+    if (p->streamed) return fail(NW_ERR_STATE, "the table of a streamed one-shot call is not resident");
     *d_table = p->d_table;
     *pitch = p->tpitch;
     return NW_OK;
@@ -934,7 +1029,7 @@ extern "C" int nw_plan_traceback(nw_plan* p, int8_t* a1, int8_t* a2, int32_t* le
 {
     if (!p || !a1 || !a2 || !len) return fail(NW_ERR_ARG, "bad argument");
     if (p->mode != NW_MODE_FULL) return fail(NW_ERR_STATE, "traceback needs a full-table plan");
-    if (p->nparts != 1) return fail(NW_ERR_UNSUPPORTED, "traceback needs the whole table on one device");
+    if (p->nparts != 1 || p->streamed) return fail(NW_ERR_UNSUPPORTED, "traceback needs the whole table on one device");
     if (p->epoch == 0) return fail(NW_ERR_STATE, "no fill has been run");
     CK(cudaSetDevice(p->device));
     const size_t cap = (size_t)p->n1 + (size_t)p->n2 + 1;
@@ -1018,7 +1113,7 @@ extern "C" int nw_cuda_init(int device)
             return fail(NW_ERR_CUDA, "self-test failed: score %d, expected %d", score, (int)a.size());
     }
     if (rc == NW_OK) {      // pinned staging for table delivery, so the first timed call does not allocate it
-        std::lock_guard<std::mutex> lk(g_stage_mu);
+        std::lock_guard<std::mutex> lk(g_stage_mus[device]);
         rc = ensure_staging(device);
     }
     if (rc == NW_OK) warmed[device] = true;
@@ -1063,7 +1158,8 @@ static int run_pipeline(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t 
         nw_tuning tune;
         memset(&tune, 0, sizeof tune);
         for (int g = 0; g < ngpus && rc == NW_OK; ++g) {
-            rc = nw_plan_create(&cache[g], g, n1, n2, mode, g, ngpus, g == 0 ? nullptr : &tune);
+            rc = plan_create_internal(&cache[g], g, n1, n2, mode, g, ngpus, g == 0 ? nullptr : &tune,
+                                      /*want_streamed=*/ngpus == 1 && mode == NW_MODE_FULL && table != nullptr);
             if (rc == NW_OK && g == 0) tune.rows_per_lane = cache[0]->R;     // all parts share the strip height
         }
         for (int g = 0; g + 1 < ngpus && rc == NW_OK; ++g) rc = nw_plan_connect(cache[g], cache[g + 1]);
@@ -1087,8 +1183,23 @@ static int run_pipeline(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t 
     for (int g = 0; g < ngpus && rc == NW_OK; ++g) rc = nw_plan_sync(plans[g]);
     tr.mark("sync (kernels done)");
     nw_plan* last = plans[(size_t)ngpus - 1];
-    if (rc == NW_OK && table && mode == NW_MODE_FULL)
-        for (int g = 0; g < ngpus && rc == NW_OK; ++g) rc = nw_plan_table_to_host(plans[g], table);
+    if (rc == NW_OK && table && mode == NW_MODE_FULL) {
+        if (ngpus == 1) rc = nw_plan_table_to_host(plans[0], table);
+        else {
+            // every part delivers its own columns over its own PCIe link, concurrently
+            std::vector<int> rcs((size_t)ngpus, NW_OK);
+            std::vector<std::string> msgs((size_t)ngpus);
+            std::vector<std::thread> th;
+            for (int g = 0; g < ngpus; ++g)
+                th.emplace_back([&, g] {
+                    rcs[g] = nw_plan_table_to_host(plans[g], table);
+                    if (rcs[g] != NW_OK) msgs[g] = g_err;          // g_err is thread-local
+                });
+            for (auto& x : th) x.join();
+            for (int g = 0; g < ngpus; ++g)
+                if (rcs[g] != NW_OK && rc == NW_OK) rc = fail(rcs[g], "%s", msgs[g].c_str());
+        }
+    }
     tr.mark("table_to_host");
     if (rc == NW_OK && score) rc = nw_plan_score(last, score);
     if (rc == NW_OK && last_col) rc = nw_plan_last_col(last, last_col);

@@ -81,6 +81,7 @@ struct StripParams {
     uint32_t* snap;         // nstrips x ntiles x 32*(R+2) words, or nullptr
     int tile_blocks;        // 32-column blocks per tile
     int ntiles;             // tiles per strip
+    int s_begin, s_count;   // pass 2: the strips this launch covers (streamed table delivery runs it band by band)
     const int* ack_in;      // producer side: the consumer's "finished epoch" word (in the consumer's mailbox
                             // allocation, possibly peer memory); the kernel waits for ack >= epoch - 2
 };

@@ -301,10 +301,11 @@ __global__ void __launch_bounds__(256) nw_full16_kernel(const StripParams p)
     const int nblocks = (ncols + 63 + 31) >> 5;
     const uint32_t upsel = (lane == 0) ? 0x1054u : 0x3210u;
     const int src_lane = (lane + 31) & 31;
-    const long long ntasks = (long long)p.nstrips * p.ntiles;
+    const long long ntasks = (long long)p.s_count * p.ntiles;
 
     for (long long task = (long long)blockIdx.x * nwarps + warp; task < ntasks; task += (long long)gridDim.x * nwarps) {
-        const int s = (int)(task / p.ntiles), m = (int)(task - (long long)s * p.ntiles);
+        const int s_rel = (int)(task / p.ntiles), m = (int)(task - (long long)s_rel * p.ntiles);
+        const int s = p.s_begin + s_rel;
         const int i_lo = s * SH + lane * R - p.pad_top;      // table row just above the low half's first row
         const int i_hi = i_lo + 32 * R;
         uint32_t sel[R];

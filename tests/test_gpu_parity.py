@@ -432,3 +432,17 @@ def test_traceback_2gb_properties(gpu):
     assert np.array_equal(a1[a1 != 0], s1) and np.array_equal(a2[a2 != 0], s2)
     gaps = int((a1 == 0).sum() + (a2 == 0).sum())
     assert int(((a1 == a2) & (a1 != 0)).sum()) - gaps == GOLDEN["fixtures"]["2gb"]["score"]
+
+
+@pytest.mark.parametrize("shape", [(5003, 3001), (2999, 6007)])
+def test_streamed_table_delivery(gpu, oracle, monkeypatch, shape):
+    # one-shot full-table calls with a host table never hold the whole table on the device: pass 2 runs band by band
+    # into a two-band ring while the previous band travels to the host.  Small bands force several of them here.
+    monkeypatch.setenv("NW_CUDA_BAND_MB", "16")
+    n1, n2 = shape
+    s1, s2 = synth_pair(55 + n1, n1, n2, 5)
+    t = np.full((n2 + 1, n1 + 1), -7, dtype=np.int32)
+    gpu.needlemanWunsch(s1, s2, t)
+    assert np.array_equal(t, oracle.fill(s1, s2))
+    gpu.needlemanWunsch(s1, s2, t)                        # cached plan, second epoch
+    assert np.array_equal(t, oracle.fill(s1, s2))

@@ -1,5 +1,6 @@
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_final_ref.json 2>&1
-python bench.py --workload batch --steps 2 --warmup 2 --batch-pairs 100000 > gpurun_out/plain_batch.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:nw_batch16 -s 2 -c 1 -o gpurun_out/prof_r01_batch16 python bench.py --workload batch --steps 2 --warmup 2 --batch-pairs 100000 > gpurun_out/ncu_batch.log 2>&1
-python bench.py --workload 2gb-full --steps 2 --warmup 2 --no-cpu-baseline > gpurun_out/plain_full.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:nw_full16 -s 2 -c 1 -o gpurun_out/prof_r01_full16_aligned python bench.py --workload 2gb-full --steps 2 --warmup 2 --no-cpu-baseline > gpurun_out/ncu_full2.log 2>&1
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain_64gb.log 2>&1 && ncu --set full --clock-control none -k regex:nw_strip16 -s 3 -c 1 -o gpurun_out/prof_r01_strip16_64gb python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_64gb2.log 2>&1
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -5 > gpurun_out/pytest17.log
+B=oracle/_ref/bdna; export NW_CUDA_TRACE=1
+for i in 1 2 3; do echo "== cuda.e 2gb full" >> gpurun_out/driver6.log; NW_CUDA_MODE=full fast-needleman-wunsch_b200/bin/cuda.e $B/2gb-1.bdna $B/2gb-2.bdna 2>&1 | grep -E "^[0-9]+$|Score|plan_create|sync|table_to" >> gpurun_out/driver6.log; done
+for i in 1 2; do echo "== cuda.e mid full" >> gpurun_out/driver6.log; NW_CUDA_MODE=full fast-needleman-wunsch_b200/bin/cuda.e $B/mid1.bdna $B/mid2.bdna 2>&1 | grep -E "^[0-9]+$|Score|plan_create|sync|table_to" >> gpurun_out/driver6.log; done
+echo "== cuda.e mid full NO_STREAMED" >> gpurun_out/driver6.log; NW_CUDA_NO_STREAMED=1 NW_CUDA_MODE=full fast-needleman-wunsch_b200/bin/cuda.e $B/mid1.bdna $B/mid2.bdna 2>&1 | grep -E "^[0-9]+$|Score|plan_create|sync|table_to" >> gpurun_out/driver6.log
+echo "== sentinel mid 16 thr" >> gpurun_out/driver6.log; OMP_NUM_THREADS=16 oracle/_ref/sentinel-otf-blocked-mt.e $B/mid1.bdna $B/mid2.bdna >> gpurun_out/driver6.log 2>&1
