@@ -335,12 +335,29 @@ def gpu_arm(args):
     else:
         table = None
 
+    # Boundary mode on one GPU delivers only the score, so the reference-facing call (nw_cuda_fill with
+    # NW_CUDA_MODE=boundary, nw_cuda_score) meets in the middle: NW_MODE_SCORE, two half-length dependency chains.
+    # It is timed on its own (score_only) and it is what the end-to-end number goes through.
+    splan, score_only = None, None
+    if world == 1 and mode == nw.NW_MODE_BOUNDARY:
+        splan = nw.Plan(n1, n2, mode=nw.NW_MODE_SCORE, device=device, rows_per_lane=args.rows_per_lane)
+        splan.upload(s1, s2)
+        splan.time(max(1, min(args.warmup, 3)))
+        so_ms = splan.time(args.steps)
+        if splan.score() != score:
+            raise SystemExit(f"bench: score-mode score {splan.score()} != {score}")
+        score_only = {"value": cells / so_ms / 1e6, "unit": "GCUPS", "ms_per_step": so_ms,
+                      "mode": "NW_MODE_SCORE: top half filled forwards, bottom half backwards, concurrently; "
+                              "H[n2][n1] = max_j F[m][j] + B[m][j]; same number of cell updates, bit-exact score",
+                      "launches_per_step": splan.launches_per_run()}
+    eplan = splan if splan is not None else plan
+
     def e2e_step():
-        plan.upload(h1, h2)                # H2D of both sequences + operand encoding
-        plan.run()
+        eplan.upload(h1, h2)               # H2D of both sequences + operand encoding
+        eplan.run()
         if table is not None:
-            plan.table_to_host(table)      # D2H of the whole table (what the reference driver's caller owns)
-        return plan.score() if rank == world - 1 else plan.sync()   # D2H of the score (driver.cpp:35 reads it)
+            eplan.table_to_host(table)     # D2H of the whole table (what the reference driver's caller owns)
+        return eplan.score() if rank == world - 1 else eplan.sync()   # D2H of the score (driver.cpp:35 reads it)
 
     barrier()
     for _ in range(min(args.warmup, 3)):
@@ -407,12 +424,17 @@ def gpu_arm(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3 / args.steps,
-                        "path": "nw_plan_upload(host s1,s2) + nw_plan_run + nw_plan_score per step"},
+                        "path": ("NW_MODE_SCORE plan: " if splan is not None else "") +
+                                "nw_plan_upload(host s1,s2) + nw_plan_run + nw_plan_score per step"},
                 "gpu_launches": launches, "roofline": roof}
+        if score_only is not None:
+            line["score_only"] = score_only
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     plan.close()
+    if splan is not None:
+        splan.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

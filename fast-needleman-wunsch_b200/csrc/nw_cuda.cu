@@ -211,6 +211,11 @@ struct nw_plan {
     cudaStream_t stream2 = nullptr;
     cudaEvent_t band_ev[2] = {nullptr, nullptr};
     nw::StripParams last_sp;         // parameters of the most recent fill (pass 2 of a streamed delivery reuses them)
+    // NW_MODE_SCORE: this plan only owns two boundary-mode sub-plans (top half forwards, bottom half reversed), a join
+    // event and the combined score
+    nw_plan* sub[2] = {nullptr, nullptr};
+    int split = 0;                   // rows of the top half
+    cudaEvent_t join_ev = nullptr;
 };
 
 static int ensure_device(int device)
@@ -317,6 +322,9 @@ extern "C" int nw_plan_destroy(nw_plan* p)
 {
     if (!p) return NW_OK;
     cudaSetDevice(p->device);
+    if (p->sub[0]) nw_plan_destroy(p->sub[0]);
+    if (p->sub[1]) nw_plan_destroy(p->sub[1]);
+    if (p->join_ev) cudaEventDestroy(p->join_ev);
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->ipc_mailbox) cudaIpcCloseMemHandle(p->ipc_mailbox);
     void* bufs[] = {p->d_s1, p->d_s2, p->d_wq, p->d_rsel, p->d_bitmap, p->d_brow, p->d_mailbox, p->d_rcol_local,
@@ -507,6 +515,31 @@ static int plan_create_internal(nw_plan** out, int device, int32_t n1, int32_t n
     if (!out) return fail(NW_ERR_ARG, "out is NULL");
     *out = nullptr;
     if (n1 < 0 || n2 < 0) return fail(NW_ERR_ARG, "negative sequence length (n1=%d, n2=%d)", n1, n2);
+    if (mode == NW_MODE_SCORE) {
+        if (nparts != 1 || part != 0) return fail(NW_ERR_UNSUPPORTED, "score mode is a single-device mode");
+        int rc0 = ensure_device(device);
+        if (rc0) return rc0;
+        nw_plan* q = new (std::nothrow) nw_plan;
+        if (!q) return fail(NW_ERR_CUDA, "out of host memory");
+        q->device = device; q->n1 = n1; q->n2 = n2; q->mode = mode;
+        q->split = n2 / 2;
+        rc0 = plan_create_internal(&q->sub[0], device, n1, q->split, NW_MODE_BOUNDARY, 0, 1, tuning, false);
+        if (rc0 == NW_OK) rc0 = plan_create_internal(&q->sub[1], device, n1, n2 - q->split, NW_MODE_BOUNDARY, 0, 1, tuning, false);
+        if (rc0 == NW_OK && cudaEventCreateWithFlags(&q->join_ev, cudaEventDisableTiming) != cudaSuccess)
+            rc0 = fail(NW_ERR_CUDA, "cudaEventCreate failed");
+        if (rc0 == NW_OK && cudaMalloc(&q->d_score, 64) != cudaSuccess) rc0 = fail(NW_ERR_CUDA, "cudaMalloc failed");
+        if (rc0 != NW_OK) {
+            char keep[512];
+            memcpy(keep, g_err, sizeof keep);
+            nw_plan_destroy(q);
+            memcpy(g_err, keep, sizeof keep);
+            return rc0;
+        }
+        q->R = q->sub[1]->R; q->warps = q->sub[1]->warps; q->nstrips = q->sub[0]->nstrips + q->sub[1]->nstrips;
+        q->ctas = q->sub[0]->ctas + q->sub[1]->ctas;
+        *out = q;
+        return NW_OK;
+    }
     if (mode != NW_MODE_BOUNDARY && mode != NW_MODE_FULL) return fail(NW_ERR_ARG, "unknown mode %d", mode);
     if (nparts < 1 || part < 0 || part >= nparts) return fail(NW_ERR_ARG, "bad part %d of %d", part, nparts);
     if (nparts > 1 && ((long long)n1 + 1) / nparts < 2)
@@ -560,6 +593,17 @@ extern "C" int nw_plan_upload(nw_plan* p, const int8_t* s1, const int8_t* s2)
 {
     if (!p) return fail(NW_ERR_ARG, "plan is NULL");
     if ((p->n1 > 0 && !s1) || (p->n2 > 0 && !s2)) return fail(NW_ERR_ARG, "sequence pointer is NULL");
+    if (p->mode == NW_MODE_SCORE) {
+        // top half: s1 against s2[0, split); bottom half: both reversed, s2[split, n2) -- the backward fill
+        std::vector<int8_t> r1((size_t)p->n1), r2((size_t)(p->n2 - p->split));
+        for (int i = 0; i < p->n1; ++i) r1[i] = s1[p->n1 - 1 - i];
+        for (int i = 0; i < p->n2 - p->split; ++i) r2[i] = s2[p->n2 - 1 - i];
+        int rc = nw_plan_upload(p->sub[0], s1, s2);
+        if (rc == NW_OK) rc = nw_plan_upload(p->sub[1], r1.data(), r2.data());
+        if (rc == NW_OK) rc = nw_plan_sync(p->sub[1]);       // r1 / r2 are about to go out of scope
+        p->uploaded = rc == NW_OK;
+        return rc;
+    }
     CK(cudaSetDevice(p->device));
     // alphabet of BOTH full sequences, so that every part of a pipeline makes the same choice of path
     bool seen[256] = {false};
@@ -575,6 +619,7 @@ extern "C" int nw_plan_upload(nw_plan* p, const int8_t* s1, const int8_t* s2)
 extern "C" int nw_plan_upload_device(nw_plan* p, const int8_t* d_s1, const int8_t* d_s2)
 {
     if (!p) return fail(NW_ERR_ARG, "plan is NULL");
+    if (p->mode == NW_MODE_SCORE) return fail(NW_ERR_UNSUPPORTED, "score mode takes host sequences (nw_plan_upload)");
     if ((p->n1 > 0 && !d_s1) || (p->n2 > 0 && !d_s2)) return fail(NW_ERR_ARG, "sequence pointer is NULL");
     CK(cudaSetDevice(p->device));
     CK(cudaMemsetAsync(p->d_bitmap, 0, 8 * sizeof(uint32_t), p->stream));
@@ -596,6 +641,7 @@ extern "C" int nw_plan_upload_device(nw_plan* p, const int8_t* d_s1, const int8_
 extern "C" int nw_plan_connect(nw_plan* left, nw_plan* right)
 {
     if (!left || !right) return fail(NW_ERR_ARG, "plan is NULL");
+    if (left->mode == NW_MODE_SCORE || right->mode == NW_MODE_SCORE) return fail(NW_ERR_UNSUPPORTED, "score mode is a single-device mode");
     if (left->nparts != right->nparts || right->part != left->part + 1 || left->n1 != right->n1 || left->n2 != right->n2)
         return fail(NW_ERR_ARG, "plans are not adjacent parts of the same pipeline");
     if (left->device != right->device) {
@@ -621,6 +667,7 @@ extern "C" int nw_plan_connect(nw_plan* left, nw_plan* right)
 extern "C" int nw_plan_export_mailbox(nw_plan* p, void* handle64)
 {
     if (!p || !handle64) return fail(NW_ERR_ARG, "NULL argument");
+    if (p->mode == NW_MODE_SCORE) return fail(NW_ERR_UNSUPPORTED, "score mode is a single-device mode");
     if (p->part == 0) return fail(NW_ERR_STATE, "part 0 has no halo mailbox");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     CK(cudaSetDevice(p->device));
@@ -634,6 +681,7 @@ extern "C" int nw_plan_export_mailbox(nw_plan* p, void* handle64)
 extern "C" int nw_plan_import_mailbox(nw_plan* p, const void* handle64, int consumer_device)
 {
     if (!p || !handle64) return fail(NW_ERR_ARG, "NULL argument");
+    if (p->mode == NW_MODE_SCORE) return fail(NW_ERR_UNSUPPORTED, "score mode is a single-device mode");
     if (p->part == p->nparts - 1) return fail(NW_ERR_STATE, "the last part has no right neighbour");
     (void)consumer_device;
     CK(cudaSetDevice(p->device));
@@ -712,10 +760,35 @@ static int plan_enqueue(nw_plan* p)
     return NW_OK;
 }
 
+// NW_MODE_SCORE: both halves on their own streams, then the combine kernel on the top half's stream
+static int score_enqueue(nw_plan* p)
+{
+    if (!p->uploaded) return fail(NW_ERR_STATE, "nw_plan_upload has not been called");
+    nw_plan *a = p->sub[0], *b = p->sub[1];
+    int rc = plan_enqueue(b);
+    if (rc == NW_OK) rc = plan_enqueue(a);
+    if (rc) return rc;
+    CK(cudaEventRecord(p->join_ev, b->stream));
+    CK(cudaStreamWaitEvent(a->stream, p->join_ev, 0));
+    nw::nw_bidir_combine_kernel<<<1, 1024, 0, a->stream>>>(a->d_last_row, b->d_last_row, p->n1, p->d_score);
+    CK(cudaGetLastError());
+    p->epoch += 1;
+    return NW_OK;
+}
+
 extern "C" int nw_plan_run(nw_plan* p)
 {
     if (!p) return fail(NW_ERR_ARG, "plan is NULL");
     CK(cudaSetDevice(p->device));
+    if (p->mode == NW_MODE_SCORE) {
+        // the bottom half's stream must not start before the timing event of the top half's stream
+        CK(cudaEventRecord(p->sub[0]->ev0, p->sub[0]->stream));
+        CK(cudaStreamWaitEvent(p->sub[1]->stream, p->sub[0]->ev0, 0));
+        int rc = score_enqueue(p);
+        if (rc) return rc;
+        CK(cudaEventRecord(p->sub[0]->ev1, p->sub[0]->stream));
+        return NW_OK;
+    }
     CK(cudaEventRecord(p->ev0, p->stream));
     int rc = plan_enqueue(p);
     if (rc) return rc;
@@ -727,6 +800,11 @@ extern "C" int nw_plan_sync(nw_plan* p)
 {
     if (!p) return fail(NW_ERR_ARG, "plan is NULL");
     CK(cudaSetDevice(p->device));
+    if (p->mode == NW_MODE_SCORE) {
+        CK(cudaStreamSynchronize(p->sub[1]->stream));
+        CK(cudaStreamSynchronize(p->sub[0]->stream));
+        return NW_OK;
+    }
     CK(cudaStreamSynchronize(p->stream));
     return NW_OK;
 }
@@ -736,6 +814,24 @@ extern "C" int nw_plan_time(nw_plan* p, int iters, float* ms_per_fill)
     if (!p || !ms_per_fill || iters < 1) return fail(NW_ERR_ARG, "bad argument");
     if (p->nparts > 1) return fail(NW_ERR_STATE, "nw_plan_time is for single-part plans; time pipelines with nw_plan_run");
     CK(cudaSetDevice(p->device));
+    if (p->mode == NW_MODE_SCORE) {
+        nw_plan *a = p->sub[0], *b = p->sub[1];
+        CK(cudaStreamSynchronize(a->stream));
+        CK(cudaStreamSynchronize(b->stream));
+        CK(cudaEventRecord(a->ev2, a->stream));
+        CK(cudaStreamWaitEvent(b->stream, a->ev2, 0));
+        for (int i = 0; i < iters; ++i) {
+            int rc = score_enqueue(p);        // every combine joins the two streams on a's
+            if (rc) return rc;
+        }
+        CK(cudaEventRecord(a->ev3, a->stream));
+        CK(cudaEventSynchronize(a->ev3));
+        CK(cudaStreamSynchronize(b->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, a->ev2, a->ev3));
+        *ms_per_fill = ms / iters;
+        return NW_OK;
+    }
     CK(cudaStreamSynchronize(p->stream));
     CK(cudaEventRecord(p->ev0, p->stream));
     for (int i = 0; i < iters; ++i) {
@@ -754,6 +850,11 @@ extern "C" int nw_plan_timer_start(nw_plan* p)
 {
     if (!p) return fail(NW_ERR_ARG, "plan is NULL");
     CK(cudaSetDevice(p->device));
+    if (p->mode == NW_MODE_SCORE) {
+        CK(cudaEventRecord(p->sub[0]->ev2, p->sub[0]->stream));
+        CK(cudaStreamWaitEvent(p->sub[1]->stream, p->sub[0]->ev2, 0));
+        return NW_OK;
+    }
     CK(cudaEventRecord(p->ev2, p->stream));
     return NW_OK;
 }
@@ -762,6 +863,13 @@ extern "C" int nw_plan_timer_stop(nw_plan* p, float* ms)
 {
     if (!p || !ms) return fail(NW_ERR_ARG, "bad argument");
     CK(cudaSetDevice(p->device));
+    if (p->mode == NW_MODE_SCORE) {          // the last combine kernel already joined both streams on sub[0]'s
+        nw_plan* a = p->sub[0];
+        CK(cudaEventRecord(a->ev3, a->stream));
+        CK(cudaEventSynchronize(a->ev3));
+        CK(cudaEventElapsedTime(ms, a->ev2, a->ev3));
+        return NW_OK;
+    }
     CK(cudaEventRecord(p->ev3, p->stream));
     CK(cudaEventSynchronize(p->ev3));
     CK(cudaEventElapsedTime(ms, p->ev2, p->ev3));
@@ -772,6 +880,7 @@ extern "C" int nw_plan_last_ms(nw_plan* p, float* ms)
 {
     if (!p || !ms) return fail(NW_ERR_ARG, "bad argument");
     CK(cudaSetDevice(p->device));
+    if (p->mode == NW_MODE_SCORE) p = p->sub[0];
     CK(cudaEventSynchronize(p->ev1));
     CK(cudaEventElapsedTime(ms, p->ev0, p->ev1));
     return NW_OK;
@@ -780,6 +889,13 @@ extern "C" int nw_plan_last_ms(nw_plan* p, float* ms)
 extern "C" int nw_plan_launches_per_run(nw_plan* p, int* n)
 {
     if (!p || !n) return fail(NW_ERR_ARG, "bad argument");
+    if (p->mode == NW_MODE_SCORE) {
+        int a = 0, b = 0;
+        nw_plan_launches_per_run(p->sub[0], &a);
+        nw_plan_launches_per_run(p->sub[1], &b);
+        *n = a + b + 1;
+        return NW_OK;
+    }
     const bool have_cells = p->ncols > 0 && p->n2 > 0;
     *n = (have_cells ? 1 : 0) + 1 + (p->mode == NW_MODE_FULL ? 1 + ((!have_cells && p->n2 > 0) ? 1 : 0) : 0) +
          ((have_cells && p->kernel2) ? 1 : 0);
@@ -792,14 +908,16 @@ extern "C" int nw_plan_score(nw_plan* p, int32_t* score)
     if (!p || !score) return fail(NW_ERR_ARG, "bad argument");
     if (p->epoch == 0) return fail(NW_ERR_STATE, "no fill has been run");
     CK(cudaSetDevice(p->device));
-    CK(cudaMemcpyAsync(score, p->d_score, sizeof(int32_t), cudaMemcpyDeviceToHost, p->stream));
-    CK(cudaStreamSynchronize(p->stream));
+    cudaStream_t st = (p->mode == NW_MODE_SCORE) ? p->sub[0]->stream : p->stream;
+    CK(cudaMemcpyAsync(score, p->d_score, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return NW_OK;
 }
 
 extern "C" int nw_plan_last_row(nw_plan* p, int32_t* last_row)
 {
     if (!p || !last_row) return fail(NW_ERR_ARG, "bad argument");
+    if (p->mode == NW_MODE_SCORE) return fail(NW_ERR_STATE, "a score-mode plan only has a score");
     if (p->epoch == 0) return fail(NW_ERR_STATE, "no fill has been run");
     CK(cudaSetDevice(p->device));
     CK(cudaMemcpyAsync(last_row, p->d_last_row, sizeof(int32_t) * ((size_t)p->ncols + 1), cudaMemcpyDeviceToHost, p->stream));
@@ -810,6 +928,7 @@ extern "C" int nw_plan_last_row(nw_plan* p, int32_t* last_row)
 extern "C" int nw_plan_last_col(nw_plan* p, int32_t* last_col)
 {
     if (!p || !last_col) return fail(NW_ERR_ARG, "bad argument");
+    if (p->mode == NW_MODE_SCORE) return fail(NW_ERR_STATE, "a score-mode plan only has a score");
     if (p->epoch == 0) return fail(NW_ERR_STATE, "no fill has been run");
     CK(cudaSetDevice(p->device));
     CK(cudaMemcpyAsync(last_col, p->d_last_col, sizeof(int32_t) * ((size_t)p->n2 + 1), cudaMemcpyDeviceToHost, p->stream));
@@ -1071,6 +1190,7 @@ extern "C" int nw_plan_strip_info(nw_plan* p, int* nstrips, int* strip_rows, int
 extern "C" int nw_plan_strip_row(nw_plan* p, int strip, int32_t* row)
 {
     if (!p || !row) return fail(NW_ERR_ARG, "bad argument");
+    if (p->mode == NW_MODE_SCORE) return fail(NW_ERR_STATE, "a score-mode plan only has a score");
     if (strip < 0 || strip >= p->nstrips) return fail(NW_ERR_ARG, "strip %d out of range (%d strips)", strip, p->nstrips);
     if (p->epoch == 0) return fail(NW_ERR_STATE, "no fill has been run");
     if (p->ncols == 0) return fail(NW_ERR_STATE, "part has no interior columns");
@@ -1215,6 +1335,29 @@ static int run_pipeline(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t 
     return rc;
 }
 
+// score only, through a cached NW_MODE_SCORE plan (what the reference driver reads in boundary mode: driver.cpp:35)
+static int run_score_oneshot(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int32_t* score)
+{
+    Trace tr;
+    static std::mutex mu;
+    static nw_plan* cached = nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    int rc = NW_OK;
+    if (!cached || cached->n1 != n1 || cached->n2 != n2) {
+        if (cached) nw_plan_destroy(cached);
+        cached = nullptr;
+        rc = nw_plan_create(&cached, 0, n1, n2, NW_MODE_SCORE, 0, 1, nullptr);
+        if (rc) return rc;
+    }
+    tr.mark("plan_create");
+    rc = nw_plan_upload(cached, s1, s2);
+    tr.mark("upload");
+    if (rc == NW_OK) rc = nw_plan_run(cached);
+    if (rc == NW_OK) rc = nw_plan_score(cached, score);
+    tr.mark("run + score");
+    return rc;
+}
+
 extern "C" int nw_cuda_fill_ex(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int32_t* table, int mode,
                                int ngpus)
 {
@@ -1223,7 +1366,8 @@ extern "C" int nw_cuda_fill_ex(const int8_t* s1, int32_t n1, const int8_t* s2, i
     if (mode == NW_MODE_FULL) return run_pipeline(s1, n1, s2, n2, mode, ngpus, table, nullptr, nullptr, nullptr);
     if (mode != NW_MODE_BOUNDARY) return fail(NW_ERR_ARG, "unknown mode %d", mode);
     int32_t score = 0;
-    int rc = run_pipeline(s1, n1, s2, n2, mode, ngpus, nullptr, nullptr, nullptr, &score);
+    int rc = (ngpus == 1 && !env_int("NW_CUDA_NO_BIDIR", 0)) ? run_score_oneshot(s1, n1, s2, n2, &score)
+                                                            : run_pipeline(s1, n1, s2, n2, mode, ngpus, nullptr, nullptr, nullptr, &score);
     if (rc == NW_OK) table[((long long)n1 + 1) * ((long long)n2 + 1) - 1] = score;     // what driver.cpp:35 reads
     return rc;
 }
@@ -1245,6 +1389,7 @@ extern "C" int nw_cuda_score(const int8_t* s1, int32_t n1, const int8_t* s2, int
 {
     if (!score) return fail(NW_ERR_ARG, "score is NULL");
     if (n1 < 0 || n2 < 0) return fail(NW_ERR_ARG, "negative sequence length");
+    if (!env_int("NW_CUDA_NO_BIDIR", 0)) return run_score_oneshot(s1, n1, s2, n2, score);
     return run_pipeline(s1, n1, s2, n2, NW_MODE_BOUNDARY, 1, nullptr, nullptr, nullptr, score);
 }
 

@@ -18,6 +18,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <limits.h>
 
 namespace nw {
 
@@ -362,6 +363,24 @@ __global__ void nw_finish_kernel(const int2* brow_last, const int2* rcol, const 
     // sits on another GPU) reuse it.  Stream order puts this kernel after the strip kernel.
     if (ack_out != nullptr && tid == 0)
         asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(ack_out), "r"(epoch) : "memory");
+}
+
+// NW_MODE_SCORE: F[j] = H of the top half's last row, B[j'] = the same for the reversed bottom half;
+// H[n2][n1] = max_j F[j] + B[n1 - j]   (one block)
+__global__ void __launch_bounds__(1024) nw_bidir_combine_kernel(const int32_t* __restrict__ F, const int32_t* __restrict__ B,
+                                                                int n1, int32_t* score)
+{
+    __shared__ int red[32];
+    int best = INT_MIN;
+    for (int j = threadIdx.x; j <= n1; j += blockDim.x) best = max(best, F[j] + B[n1 - j]);
+    best = __reduce_max_sync(FULL_MASK, best);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : INT_MIN;
+        v = __reduce_max_sync(FULL_MASK, v);
+        if (threadIdx.x == 0) *score = v;
+    }
 }
 
 // strip boundary row k in H form (checkpoint rows kept in HBM)

@@ -11,6 +11,7 @@ import numpy as np
 
 NW_MODE_BOUNDARY = 0
 NW_MODE_FULL = 1
+NW_MODE_SCORE = 2      # score only, meeting in the middle (two half-length dependency chains)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 lib_path = os.environ.get("NW_CUDA_LIB", os.path.join(_HERE, "libnw_cuda.so"))   # override: A/B builds in development

@@ -37,6 +37,10 @@ extern "C" {
 /* memory modes (BASELINE.json configs[2]) */
 #define NW_MODE_BOUNDARY 0    /* keep strip boundary rows + right column only; host gets the score        */
 #define NW_MODE_FULL 1        /* materialise every cell, as the reference does (src/serial/serial.cpp:31)    */
+#define NW_MODE_SCORE 2       /* score only, meeting in the middle: the top half of the table is filled forwards and,
+                                 concurrently, the bottom half backwards (= forwards on the reversed sequences);
+                                 H[n2][n1] = max_j F[m][j] + B[m][j].  Two dependency chains of half the length
+                                 instead of one; only nw_plan_score is available on such a plan                 */
 
 /* ------------------------------------------------------------------------------------------------------------
  * Library / device
@@ -57,7 +61,8 @@ int nw_cuda_device_info(int device, char* name, int name_len, int* sm_count, int
 /* Replaces needlemanWunsch(dnaArray,dnaArray,int*) (src/serial/serial.cpp:4-36).
  * table: caller-owned HOST memory, (n2+1)*(n1+1) int32 (src/common/driver.cpp:19-23).
  * Mode and GPU count come from the environment (the driver's argv is fixed, src/common/driver.cpp:2):
- *   NW_CUDA_MODE = full (default: every cell written, like the reference) | boundary (only table[size-1])
+ *   NW_CUDA_MODE = full (default: every cell written, like the reference) | boundary (only table[size-1], computed
+ *                  in NW_MODE_SCORE fashion)
  *   NW_CUDA_GPUS = 1 (default) | 2 | 4 | 8   column strips across devices of this process */
 int nw_cuda_fill(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int32_t* table);
 int nw_cuda_fill_ex(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int32_t* table,

@@ -446,3 +446,40 @@ def test_streamed_table_delivery(gpu, oracle, monkeypatch, shape):
     assert np.array_equal(t, oracle.fill(s1, s2))
     gpu.needlemanWunsch(s1, s2, t)                        # cached plan, second epoch
     assert np.array_equal(t, oracle.fill(s1, s2))
+
+
+# ---- score-only mode: meeting in the middle -------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(0, 0), (0, 5), (5, 0), (1, 1), (1, 2), (40, 3), (3, 40), (700, 701), (5000, 2999),
+                                   (2999, 5000)])
+def test_score_mode_shapes(gpu, oracle, shape, kernel_kind):
+    n1, n2 = shape
+    s1, s2 = synth_pair(300 + n1 + 5 * n2, n1, n2, 5)
+    with gpu.Plan(n1, n2, mode=gpu.NW_MODE_SCORE) as p:
+        p.upload(s1, s2)
+        p.run()
+        assert p.score() == oracle.score(s1, s2)
+        p.run(); p.run()
+        assert p.score() == oracle.score(s1, s2)
+        assert p.time(2) > 0
+        with pytest.raises(gpu.NwCudaError):
+            p.last_row()
+    assert gpu.score(s1, s2) == oracle.score(s1, s2)          # the one-shot call uses the same mode
+
+
+@pytest.mark.parametrize("name", ["smid", "2gb", "mid", "big", "64gb"])
+def test_score_mode_fixtures(gpu, name):
+    s1, s2 = load_pair(name)
+    with gpu.Plan(s1.size, s2.size, mode=gpu.NW_MODE_SCORE) as p:
+        p.upload(s1, s2)
+        p.run()
+        assert p.score() == GOLDEN["fixtures"][name]["score"]
+
+
+def test_score_mode_generic_alphabet(gpu, oracle):
+    rng = np.random.default_rng(17)
+    s1 = rng.integers(-128, 128, size=1500, dtype=np.int8)
+    s2 = np.concatenate([s1[:600], rng.integers(-128, 128, size=900, dtype=np.int8)]).astype(np.int8)
+    with gpu.Plan(s1.size, s2.size, mode=gpu.NW_MODE_SCORE) as p:
+        p.upload(s1, s2)
+        p.run()
+        assert p.score() == oracle.score(s1, s2)
