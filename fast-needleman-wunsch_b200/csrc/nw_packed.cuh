@@ -45,13 +45,11 @@ __device__ __forceinline__ void sweep16(uint32_t (&h)[R], uint32_t& dprev, const
         const uint32_t cl[4] = {clo.x, clo.y, clo.z, clo.w};
         const uint32_t ch[4] = {chi.x, chi.y, chi.z, chi.w};
         const uint32_t tn[4] = {tin.x, tin.y, tin.z, tin.w};
-#ifndef NW_DBG_NO_LDS
         if (k4 < 7) {
             clo = *reinterpret_cast<const uint4*>(ringm + ((i0 + 4 * k4 + 4) & 127));
             chi = *reinterpret_cast<const uint4*>(ringm + ((i0 + 4 * k4 + 4 - 32) & 127));
             tin = *reinterpret_cast<const uint4*>(sin + 4 * k4 + 4);
         }
-#endif
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             const int k = 4 * k4 + kk;
@@ -104,9 +102,7 @@ __device__ __forceinline__ void sweep16(uint32_t (&h)[R], uint32_t& dprev, const
                 }
                 scar = __shfl_sync(FULL_MASK, h[R - 1], src_lane);
             }
-#ifndef NW_DBG_NO_STS
             if (lane == 31) sout[k] = h[R - 1];
-#endif
             if (TILE) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) tile_lane[r * TILE_ROW_WORDS + 8 + k] = h[r];
