@@ -92,12 +92,16 @@ int nw_cuda_batch_scores(const int8_t* S1, const int8_t* S2, int64_t npairs, int
 typedef struct nw_plan nw_plan;
 
 typedef struct nw_tuning {
-    int rows_per_lane;   /* R: rows of the table held in registers per lane; 0 = choose automatically */
+    int rows_per_lane;   /* table rows per lane (a strip is 32 x this many rows): 1, 2, 4, 8 for the 32-bit kernels,
+                            2, 4, 8, 16 for the packed s16x2 kernels (two rows per register); 0 = automatic */
     int warps_per_cta;   /* 0 = automatic */
     int ctas;            /* persistent grid size; 0 = automatic (<= resident capacity of the device) */
     int reserved[5];
 } nw_tuning;
 
+/* mode: NW_MODE_BOUNDARY, NW_MODE_FULL or NW_MODE_SCORE (single part only; offers nw_plan_upload / run / sync / time /
+ * score).  Kernel choice is automatic: packed s16x2 kernels when at most four distinct byte values occur in the two
+ * sequences (always true for bdna), 32-bit kernels otherwise. */
 int nw_plan_create(nw_plan** out, int device, int32_t n1, int32_t n2, int mode,
                    int part, int nparts, const nw_tuning* tuning /* may be NULL */);
 int nw_plan_destroy(nw_plan* p);
