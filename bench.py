@@ -420,7 +420,10 @@ def gpu_arm(args):
                            "nstrips": info["nstrips"], "ctas": info["ctas"], "warps_per_cta": info["warps"],
                            "l2": "no flush: the boundary-row working set (%.0f MB per fill) exceeds the 126 MB L2; "
                                  "inputs are 0.25 MB" % (hbm_bytes / 2 / 1e6),
-                           "score": score, "wall_ms_per_step": t_wall * 1e3 / args.steps},
+                           "score": score, "wall_ms_per_step": t_wall * 1e3 / args.steps,
+                           "modes": "value = one forward fill that keeps every strip boundary row and the last row/column "
+                                    "(NW_MODE_BOUNDARY plan, column strips over the GPUs); score_only and, on one GPU, e2e = "
+                                    "the score-only path the reference-facing call takes in boundary mode (NW_MODE_SCORE)"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3 / args.steps,
