@@ -217,6 +217,7 @@ struct nw_plan {
     nw_plan* sub[2] = {nullptr, nullptr};
     int split = 0;                   // rows of the top half
     cudaEvent_t join_ev = nullptr;
+    std::vector<int8_t> rev1, rev2;  // the reversed sequences of the bottom half (kept alive for the async H2D)
 };
 
 static int ensure_device(int device)
@@ -596,12 +597,15 @@ extern "C" int nw_plan_upload(nw_plan* p, const int8_t* s1, const int8_t* s2)
     if ((p->n1 > 0 && !s1) || (p->n2 > 0 && !s2)) return fail(NW_ERR_ARG, "sequence pointer is NULL");
     if (p->mode == NW_MODE_SCORE) {
         // top half: s1 against s2[0, split); bottom half: both reversed, s2[split, n2) -- the backward fill
-        std::vector<int8_t> r1((size_t)p->n1), r2((size_t)(p->n2 - p->split));
-        for (int i = 0; i < p->n1; ++i) r1[i] = s1[p->n1 - 1 - i];
-        for (int i = 0; i < p->n2 - p->split; ++i) r2[i] = s2[p->n2 - 1 - i];
+        // (a previous upload's copies have completed by now: every run is followed by a score read-back or a sync
+        //  before the caller can hand in new sequences; be safe anyway)
+        CK(cudaStreamSynchronize(p->sub[1]->stream));
+        p->rev1.resize((size_t)p->n1);
+        p->rev2.resize((size_t)(p->n2 - p->split));
+        for (int i = 0; i < p->n1; ++i) p->rev1[i] = s1[p->n1 - 1 - i];
+        for (int i = 0; i < p->n2 - p->split; ++i) p->rev2[i] = s2[p->n2 - 1 - i];
         int rc = nw_plan_upload(p->sub[0], s1, s2);
-        if (rc == NW_OK) rc = nw_plan_upload(p->sub[1], r1.data(), r2.data());
-        if (rc == NW_OK) rc = nw_plan_sync(p->sub[1]);       // r1 / r2 are about to go out of scope
+        if (rc == NW_OK) rc = nw_plan_upload(p->sub[1], p->rev1.data(), p->rev2.data());
         p->uploaded = rc == NW_OK;
         return rc;
     }
@@ -771,7 +775,9 @@ static int score_enqueue(nw_plan* p)
     if (rc) return rc;
     CK(cudaEventRecord(p->join_ev, b->stream));
     CK(cudaStreamWaitEvent(a->stream, p->join_ev, 0));
-    nw::nw_bidir_combine_kernel<<<1, 1024, 0, a->stream>>>(a->d_last_row, b->d_last_row, p->n1, p->d_score);
+    nw::nw_set_int_kernel<<<1, 1, 0, a->stream>>>(p->d_score, INT_MIN);
+    nw::nw_bidir_combine_kernel<<<std::max(1, std::min(148, (p->n1 + 256) / 256)), 256, 0, a->stream>>>(a->d_last_row, b->d_last_row,
+                                                                                                  p->n1, p->d_score);
     CK(cudaGetLastError());
     p->epoch += 1;
     return NW_OK;
@@ -894,7 +900,7 @@ extern "C" int nw_plan_launches_per_run(nw_plan* p, int* n)
         int a = 0, b = 0;
         nw_plan_launches_per_run(p->sub[0], &a);
         nw_plan_launches_per_run(p->sub[1], &b);
-        *n = a + b + 1;
+        *n = a + b + 2;
         return NW_OK;
     }
     const bool have_cells = p->ncols > 0 && p->n2 > 0;

@@ -367,19 +367,21 @@ __global__ void nw_finish_kernel(const int2* brow_last, const int2* rcol, const 
 
 // NW_MODE_SCORE: F[j] = H of the top half's last row, B[j'] = the same for the reversed bottom half;
 // H[n2][n1] = max_j F[j] + B[n1 - j]   (one block)
-__global__ void __launch_bounds__(1024) nw_bidir_combine_kernel(const int32_t* __restrict__ F, const int32_t* __restrict__ B,
-                                                                int n1, int32_t* score)
+__global__ void nw_set_int_kernel(int32_t* p, int32_t v) { *p = v; }
+
+__global__ void __launch_bounds__(256) nw_bidir_combine_kernel(const int32_t* __restrict__ F, const int32_t* __restrict__ B,
+                                                               int n1, int32_t* score /* preset to INT_MIN */)
 {
-    __shared__ int red[32];
+    __shared__ int red[8];
     int best = INT_MIN;
-    for (int j = threadIdx.x; j <= n1; j += blockDim.x) best = max(best, F[j] + B[n1 - j]);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= n1; j += gridDim.x * blockDim.x) best = max(best, F[j] + B[n1 - j]);
     best = __reduce_max_sync(FULL_MASK, best);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
     __syncthreads();
     if (threadIdx.x < 32) {
         int v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : INT_MIN;
         v = __reduce_max_sync(FULL_MASK, v);
-        if (threadIdx.x == 0) *score = v;
+        if (threadIdx.x == 0 && v != INT_MIN) atomicMax(score, v);
     }
 }
 

@@ -1,1 +1,2 @@
-python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain_final.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_r01_final_64gb.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_final.log 2>&1
+timeout 300 python -m pytest tests -x -q -m gpu -k "score" 2>&1 | tail -3 > gpurun_out/pytest20.log
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_final3.json 2>&1
