@@ -1,2 +1,2 @@
-timeout 300 python -m pytest tests -x -q -m gpu -k "score" 2>&1 | tail -3 > gpurun_out/pytest20.log
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_final3.json 2>&1
+export NW_CUDA_K2=0 NW_CUDA_LIB=$PWD/build/libnw_t.so
+timeout 60 python tools/micro3.py 2>&1 | sort | uniq -c > gpurun_out/abl7.log
