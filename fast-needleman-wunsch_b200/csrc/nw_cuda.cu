@@ -216,6 +216,7 @@ struct nw_plan {
     // event and the combined score
     nw_plan* sub[2] = {nullptr, nullptr};
     int split = 0;                   // rows of the top half
+    bool swapped = false;            // score mode sweeps along the SHORTER sequence (the score is symmetric in s1, s2)
     cudaEvent_t join_ev = nullptr;
     std::vector<int8_t> rev1, rev2;  // the reversed sequences of the bottom half (kept alive for the async H2D)
 };
@@ -523,6 +524,9 @@ static int plan_create_internal(nw_plan** out, int device, int32_t n1, int32_t n
         if (rc0) return rc0;
         nw_plan* q = new (std::nothrow) nw_plan;
         if (!q) return fail(NW_ERR_CUDA, "out of host memory");
+        // a column costs a full step of the critical path, a row only 1/256 of a strip's start-up lag: columns = shorter one
+        q->swapped = n1 > n2 && !env_int("NW_CUDA_NO_SWAP", 0);
+        if (q->swapped) std::swap(n1, n2);
         q->device = device; q->n1 = n1; q->n2 = n2; q->mode = mode;
         q->split = n2 / 2;
         rc0 = plan_create_internal(&q->sub[0], device, n1, q->split, NW_MODE_BOUNDARY, 0, 1, tuning, false);
@@ -594,6 +598,7 @@ static int plan_encode(nw_plan* p, const bool seen[256])
 extern "C" int nw_plan_upload(nw_plan* p, const int8_t* s1, const int8_t* s2)
 {
     if (!p) return fail(NW_ERR_ARG, "plan is NULL");
+    if (p->mode == NW_MODE_SCORE && p->swapped) std::swap(s1, s2);
     if ((p->n1 > 0 && !s1) || (p->n2 > 0 && !s2)) return fail(NW_ERR_ARG, "sequence pointer is NULL");
     if (p->mode == NW_MODE_SCORE) {
         // top half: s1 against s2[0, split); bottom half: both reversed, s2[split, n2) -- the backward fill
@@ -1372,13 +1377,17 @@ static int run_score_oneshot(const int8_t* s1, int32_t n1, const int8_t* s2, int
     Trace tr;
     static std::mutex mu;
     static nw_plan* cached = nullptr;
+    static int c_n1 = -1, c_n2 = -1;         // the caller's sizes (a score plan may hold them swapped)
     std::lock_guard<std::mutex> lk(mu);
     int rc = NW_OK;
-    if (!cached || cached->n1 != n1 || cached->n2 != n2) {
+    if (!cached || c_n1 != n1 || c_n2 != n2) {
         if (cached) nw_plan_destroy(cached);
         cached = nullptr;
+        c_n1 = c_n2 = -1;
         rc = nw_plan_create(&cached, 0, n1, n2, NW_MODE_SCORE, 0, 1, nullptr);
         if (rc) return rc;
+        c_n1 = n1;
+        c_n2 = n2;
     }
     tr.mark("plan_create");
     rc = nw_plan_upload(cached, s1, s2);

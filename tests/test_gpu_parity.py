@@ -483,3 +483,10 @@ def test_score_mode_generic_alphabet(gpu, oracle):
         p.upload(s1, s2)
         p.run()
         assert p.score() == oracle.score(s1, s2)
+
+
+def test_score_mode_rectangular(gpu, oracle):
+    # score mode sweeps along the shorter sequence (the score is symmetric); both orientations, extreme aspect ratios
+    for n1, n2 in [(30000, 300), (300, 30000), (9000, 1), (1, 9000), (5000, 0), (0, 5000)]:
+        s1, s2 = synth_pair(n1 + 2 * n2, n1, n2, 5)
+        assert gpu.score(s1, s2) == oracle.score(s1, s2), (n1, n2)
