@@ -10,6 +10,7 @@
 #include "nw_packed.cuh"
 #include "nw_batch.cuh"
 #include "nw_packed2.cuh"
+#include "nw_lag2.cuh"
 
 #include <cooperative_groups.h>
 #include <algorithm>
@@ -85,6 +86,17 @@ StripKernel strip16_kernel(int regs)
     case 2: return nw::nw_strip16_kernel<2>;
     case 4: return nw::nw_strip16_kernel<4>;
     case 8: return nw::nw_strip16_kernel<8>;
+    default: return nullptr;
+    }
+}
+
+StripKernel strip16l2_kernel(int regs)
+{
+    switch (regs) {
+    case 1: return nw::nw_strip16l2_kernel<1>;
+    case 2: return nw::nw_strip16l2_kernel<2>;
+    case 4: return nw::nw_strip16l2_kernel<4>;
+    case 8: return nw::nw_strip16l2_kernel<8>;
     default: return nullptr;
     }
 }
@@ -176,6 +188,7 @@ struct nw_plan {
     int warps = 8, ctas = 0, nstrips = 0, pad_top = 0;
     bool packed = false;  // nw_packed.cuh kernel (boundary mode, at most four distinct byte values)
     bool k2 = false;      // nw_packed2.cuh: two columns per step (boundary mode, wide tables)
+    bool lag2 = false;    // nw_lag2.cuh: virtual lanes two columns apart (boundary mode; the default packed kernel)
     bool generic = false, uploaded = false;
     size_t rsel_words = 0, brow_words = 0;
     int epoch = 0;
@@ -368,7 +381,7 @@ static int plan_alloc(nw_plan* p, const nw_tuning* tuning)
     const int nc = p->ncols, n2 = p->n2;
     CK(cudaMalloc(&p->d_s1, (size_t)std::max(nc, 1)));
     CK(cudaMalloc(&p->d_s2, (size_t)std::max(n2, 1)));
-    CK(cudaMalloc(&p->d_wq, sizeof(uint32_t) * ((size_t)nc + 2 * nw::WQ_PAD)));
+    CK(cudaMalloc(&p->d_wq, sizeof(uint32_t) * ((size_t)nc + nw::WQ_PAD + nw::WQ_PADR)));
     CK(cudaMalloc(&p->d_bitmap, 8 * sizeof(uint32_t)));
     p->pitch = ((long long)nc + 1 + 15) & ~15LL;
     p->mpitch = ((long long)n2 + 1 + 15) & ~15LL;
@@ -426,9 +439,13 @@ static int plan_pick_kernel(nw_plan* p)
     {
         const int k2env = env_int("NW_CUDA_K2", -1);
         p->k2 = p->packed && p->mode == NW_MODE_BOUNDARY &&
-                (k2env >= 0 ? k2env != 0 : (long long)p->ncols >= 1200LL * std::max(1, p->nstrips));
+                k2env > 0;      // superseded by the lag-2 kernel (nw_lag2.cuh); kept selectable for A/B runs
     }
-    if (p->packed && p->k2) {
+    p->lag2 = p->packed && !p->k2 && p->mode == NW_MODE_BOUNDARY && env_int("NW_CUDA_LAG2", 1) != 0;
+    if (p->lag2) {
+        p->kernel = strip16l2_kernel(R / 2);
+        p->smem = sizeof(uint32_t) * nw::L2_SMEM_WORDS_PER_WARP * (size_t)p->warps;
+    } else if (p->packed && p->k2) {
         p->kernel = strip16k2_kernel(R / 2);
         p->smem = sizeof(uint32_t) * nw::SMEM16K2_WORDS_PER_WARP * (size_t)p->warps;
     } else if (p->packed) {

@@ -22,7 +22,8 @@
 
 namespace nw {
 
-constexpr int WQ_PAD = 64;          // the column operand array is addressable for col in [-WQ_PAD, ncols + WQ_PAD)
+constexpr int WQ_PAD = 64;          // the column operand array is addressable for col in [-WQ_PAD, ncols + WQ_PADR)
+constexpr int WQ_PADR = 384;        // (the lag-2 kernel of nw_lag2.cuh prefetches up to ~260 columns past the last one)
 constexpr unsigned FULL_MASK = 0xffffffffu;
 constexpr int SMEM_WORDS_PER_WARP = 128;   // 64 column operands + 32 top-row inputs + 32 bottom-row outputs
 
@@ -33,31 +34,38 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
     return d;
 }
-// L1-bypassing loads/stores of tagged words {tag, value}
+// L1-bypassing loads/stores of tagged words {tag, value}.  Each is ONE scalar 64-bit access: PTX guarantees single-copy
+// atomicity for an aligned scalar access of up to 64 bits (a .v2.s32 access is formally two 32-bit accesses), so a
+// reader sees either the old pair or the new pair, never a mix -- the hand-off needs no flag and no fence.
+__device__ __forceinline__ int2 unpack_tagged(unsigned long long v) { return make_int2((int)(uint32_t)v, (int)(uint32_t)(v >> 32)); }
+__device__ __forceinline__ unsigned long long pack_tagged(int tag, int val)
+{
+    return (unsigned long long)(uint32_t)tag | ((unsigned long long)(uint32_t)val << 32);
+}
 __device__ __forceinline__ int2 ld_tagged_gpu(const int2* p)
 {
-    int2 v;
-    asm volatile("ld.relaxed.gpu.global.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
-    return v;
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return unpack_tagged(v);
 }
 __device__ __forceinline__ int2 ld_tagged_sys(const int2* p)
 {
-    int2 v;
-    asm volatile("ld.relaxed.sys.global.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
-    return v;
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return unpack_tagged(v);
 }
 __device__ __forceinline__ void st_tagged_gpu(int2* p, int tag, int val)
 {
-    asm volatile("st.relaxed.gpu.global.v2.s32 [%0], {%1,%2};" ::"l"(p), "r"(tag), "r"(val) : "memory");
+    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(pack_tagged(tag, val)) : "memory");
 }
 __device__ __forceinline__ void st_tagged_sys(int2* p, int tag, int val)
 {
-    asm volatile("st.relaxed.sys.global.v2.s32 [%0], {%1,%2};" ::"l"(p), "r"(tag), "r"(val) : "memory");
+    asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(p), "l"(pack_tagged(tag, val)) : "memory");
 }
 
 // ---- kernel parameters ----------------------------------------------------------------------------------------
 struct StripParams {
-    const uint32_t* wq;     // column operand per interior column c (0-based), valid for c in [-WQ_PAD, ncols+WQ_PAD)
+    const uint32_t* wq;     // column operand per interior column c (0-based), valid for c in [-WQ_PAD, ncols+WQ_PADR)
                             //   4-letter path: bytes b=0..3 hold 2 + (code(s1[c]) == b);  generic path: the raw byte
     const uint32_t* rsel;   // row operand per padded row q in [0, nstrips*32*R)
                             //   4-letter path: PRMT selector (0x5550|code real rows, 0xCCCC virtual rows)
@@ -279,7 +287,7 @@ __global__ void nw_presence_kernel(const uint8_t* s, int n, uint32_t* bitmap /*8
 struct EncodeParams {
     const uint8_t* s1;      // this part's slice: ncols bytes
     const uint8_t* s2;      // n2 bytes
-    uint32_t* wq_base;      // ncols + 2*WQ_PAD words (index c + WQ_PAD)
+    uint32_t* wq_base;      // ncols + WQ_PAD + WQ_PADR words (index c + WQ_PAD); the padding is the zero-weight word
     uint32_t* rsel;         // nrows_padded words
     int ncols, n2, nrows_padded, pad_top;
     int generic;
@@ -290,11 +298,11 @@ struct EncodeParams {
 __global__ void nw_encode_kernel(const EncodeParams e)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    for (int x = tid; x < e.ncols + 2 * WQ_PAD; x += nth) {
+    for (int x = tid; x < e.ncols + WQ_PAD + WQ_PADR; x += nth) {
         const int c = x - WQ_PAD;
         uint32_t v;
         if (c >= 0 && c < e.ncols) v = e.generic ? (uint32_t)e.s1[c] : 0x02020202u + (1u << (8 * e.code[e.s1[c]]));
-        else v = e.generic ? 0x100u : 0x02020202u;
+        else v = e.generic ? 0x100u : 0u;      // weight 0: a virtual column repeats its left neighbour (nw_lag2.cuh)
         e.wq_base[x] = v;
     }
     if (e.packed_regs > 0) {
