@@ -93,7 +93,59 @@ struct StripParams {
     int s_begin, s_count;   // pass 2: the strips this launch covers (streamed table delivery runs it band by band)
     const int* ack_in;      // producer side: the consumer's "finished epoch" word (in the consumer's mailbox
                             // allocation, possibly peer memory); the kernel waits for ack >= epoch - 2
+    int* abort_flag;             // device word + mapped host word: a wait that exceeds spin_ns sets both and gives up (the
+    int* abort_host;             // fill's results are then garbage and the host reports NW_ERR_CUDA) -- a failed peer must
+    unsigned long long spin_ns;  // not hang us.  Waiting warps re-read only the DEVICE word (a host read costs microseconds).
+    unsigned long long* times;   // nstrips x 4: %globaltimer (ns) when a strip has its first top-row block and when it
+                                 // ends, then clock64 (SM cycles) at the same two points -- the trace behind the start-up
+                                 // lag numbers and the SM clock actually seen (nw_plan_strip_times); or nullptr
 };
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Bounded spinning: every wait loop of the strip kernels calls expired() once per failed poll; after spin_ns of waiting (or
+// when another warp has already given up) it returns true and the caller leaves the loop.
+struct SpinGuard {
+    unsigned long long t0 = 0;
+    unsigned n = 0;
+    __device__ __forceinline__ bool expired(const StripParams& p)
+    {
+        if ((++n & 1023u) != 0 || p.abort_flag == nullptr) return false;
+        int a;
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(a) : "l"(p.abort_flag) : "memory");
+        if (a != 0) return true;
+        const unsigned long long t = global_ns();
+        if (t0 == 0) {
+            t0 = t;
+            return false;
+        }
+        if (t - t0 < p.spin_ns) return false;
+        asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p.abort_flag), "r"(1) : "memory");
+        asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p.abort_host), "r"(1) : "memory");
+        return true;
+    }
+};
+
+// producer side of a column-strip pipeline: do not overwrite a mailbox the consumer has not finished reading
+__device__ __forceinline__ void wait_mailbox_free(const StripParams& p)
+{
+    if (p.ack_in != nullptr) {
+        if (threadIdx.x == 0) {
+            int a;
+            SpinGuard sg;
+            do {
+                asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(a) : "l"(p.ack_in) : "memory");
+                if (a < p.epoch - 2) __nanosleep(500);
+            } while (a < p.epoch - 2 && !sg.expired(p));
+        }
+        __syncthreads();
+    }
+}
 
 // ---- the strip sweep -------------------------------------------------------------------------------------------
 template <int R, bool GENERIC>
@@ -165,10 +217,11 @@ __device__ __forceinline__ void run_strip(const StripParams& p, const int s, con
             int v = 0;
             if (i >= 1) {
                 int2 t;
+                SpinGuard sg;
                 do {
                     t = p.halo_sys ? ld_tagged_sys(p.halo + i) : ld_tagged_gpu(p.halo + i);
-                    if (t.x != p.epoch) __nanosleep(200);
-                } while (t.x != p.epoch);
+                    if (t.x != p.epoch) __nanosleep(100);
+                } while (t.x != p.epoch && !sg.expired(p));
                 v = t.y;
             }
             if (r < 0) dprev = v; else h[r] = v;
@@ -215,9 +268,11 @@ __device__ __forceinline__ void run_strip(const StripParams& p, const int s, con
         if (s > 0 && cb < ncols) {
             const int col = cb + lane;
             const bool need = col < ncols;
+            SpinGuard sg;
             while (!__all_sync(FULL_MASK, !need || pre.x == p.epoch)) {
                 __nanosleep(100);
                 if (need && pre.x != p.epoch) pre = ld_tagged_gpu(tin + col + 1);
+                if (__any_sync(FULL_MASK, sg.expired(p))) break;
             }
             sin[lane] = pre.y;
             if (col + 32 < ncols) pre = ld_tagged_gpu(tin + col + 33);
@@ -256,16 +311,7 @@ __global__ void __launch_bounds__(512) nw_strip_kernel(const StripParams p)
     int* sin = (int*)(W + 64);
     int* sout = sin + 32;
     const int slot = blockIdx.x * nwarps + warp, nslots = gridDim.x * nwarps;
-    if (p.ack_in != nullptr) {          // do not overwrite a mailbox the consumer has not finished reading
-        if (threadIdx.x == 0) {
-            int a;
-            do {
-                asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(a) : "l"(p.ack_in) : "memory");
-                if (a < p.epoch - 2) __nanosleep(500);
-            } while (a < p.epoch - 2);
-        }
-        __syncthreads();
-    }
+    wait_mailbox_free(p);
     for (int s = slot; s < p.nstrips; s += nslots) run_strip<R, GENERIC, FULL>(p, s, lane, W, sin, sout);
 }
 
@@ -292,18 +338,39 @@ struct EncodeParams {
     int ncols, n2, nrows_padded, pad_top;
     int generic;
     int packed_regs;        // 0: 32-bit kernels; R > 0: packed kernel with R registers per lane (strip = 64*R rows)
+    int lag2;               // packed lag-2 kernel (nw_lag2.cuh): the roles of row and column operands are swapped
     uint8_t code[256];      // 4-letter path: byte value -> 0..3
 };
 
 __global__ void nw_encode_kernel(const EncodeParams e)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    for (int x = tid; x < e.ncols + WQ_PAD + WQ_PADR; x += nth) {
+    for (int x = tid; x < e.ncols + WQ_PAD + WQ_PADR && !(e.packed_regs > 0 && e.lag2); x += nth) {
         const int c = x - WQ_PAD;
         uint32_t v;
         if (c >= 0 && c < e.ncols) v = e.generic ? (uint32_t)e.s1[c] : 0x02020202u + (1u << (8 * e.code[e.s1[c]]));
         else v = e.generic ? 0x100u : 0u;      // weight 0: a virtual column repeats its left neighbour (nw_lag2.cuh)
         e.wq_base[x] = v;
+    }
+    if (e.packed_regs > 0 && e.lag2) {
+        // lag-2 kernel (nw_lag2.cuh): w = PRMT(A, B, S).  Per (strip, lane, register) two row words A (low half's row) and B
+        // (high half's row) with byte b = 2 + (code(row letter) == b), zero for a virtual row; per column c ONE selector
+        // S[c] for the pair of columns (c, c - 64) the two halves of a lane work on: nibble 0 = code(s1[c]) picks A's byte,
+        // nibble 2 = 4 + code(s1[c-64]) picks B's; nibbles 1, 3 and those of a virtual column replicate a sign bit = 0
+        const int R = e.packed_regs;
+        for (int x = tid; x < e.ncols + WQ_PAD + WQ_PADR; x += nth) {
+            const int c = x - WQ_PAD, c2 = c - 64;
+            const uint32_t n0 = (c >= 0 && c < e.ncols) ? e.code[e.s1[c]] : 0x8u;
+            const uint32_t n2 = (c2 >= 0 && c2 < e.ncols) ? 4u + e.code[e.s1[c2]] : 0xCu;
+            e.wq_base[x] = n0 | 0x80u | (n2 << 8) | 0xC000u;
+        }
+        for (int x = tid; x < e.nrows_padded / 2; x += nth) {
+            const int s = x / (32 * R), rem = x - s * 32 * R, L = rem / R, r = rem - L * R;
+            const int klo = s * 64 * R + L * R + r - e.pad_top, khi = klo + 32 * R;
+            e.rsel[2 * x] = (klo >= 0) ? 0x02020202u + (1u << (8 * e.code[e.s2[klo]])) : 0u;
+            e.rsel[2 * x + 1] = (khi >= 0) ? 0x02020202u + (1u << (8 * e.code[e.s2[khi]])) : 0u;
+        }
+        return;
     }
     if (e.packed_regs > 0) {
         // packed kernel (nw_packed.cuh): one PRMT selector per (strip, lane, register): nibble 0 picks the low half's
@@ -371,6 +438,12 @@ __global__ void nw_finish_kernel(const int2* brow_last, const int2* rcol, const 
     // sits on another GPU) reuse it.  Stream order puts this kernel after the strip kernel.
     if (ack_out != nullptr && tid == 0)
         asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(ack_out), "r"(epoch) : "memory");
+}
+
+// dst[i] = src[n-1-i]: the bottom half of a score-mode plan runs forwards on both sequences reversed
+__global__ void nw_reverse_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[n - 1 - i];
 }
 
 // NW_MODE_SCORE: F[j] = H of the top half's last row, B[j'] = the same for the reversed bottom half;

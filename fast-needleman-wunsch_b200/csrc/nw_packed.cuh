@@ -111,13 +111,14 @@ __device__ __forceinline__ void sweep16(uint32_t (&h)[R], uint32_t& dprev, const
     }
 }
 
-__device__ __forceinline__ int2 poll_tagged(const int2* p, int epoch, int sys)
+__device__ __forceinline__ int2 poll_tagged(const StripParams& sp, const int2* p, int epoch, int sys)
 {
     int2 t;
+    SpinGuard sg;
     for (;;) {
         t = sys ? ld_tagged_sys(p) : ld_tagged_gpu(p);
-        if (t.x == epoch) return t;
-        __nanosleep(200);
+        if (t.x == epoch || sg.expired(sp)) return t;
+        __nanosleep(100);
     }
 }
 
@@ -153,8 +154,8 @@ __device__ __forceinline__ void run_strip16(const StripParams& p, const int s, c
 #pragma unroll
         for (int r = -1; r < R; ++r) {
             const int a = i_lo + 1 + r, b = i_hi + 1 + r;
-            lo[r + 1] = (a >= 1) ? poll_tagged(p.halo + a, p.epoch, p.halo_sys).y : 0;
-            hi[r + 1] = (b >= 1) ? poll_tagged(p.halo + b, p.epoch, p.halo_sys).y : 0;
+            lo[r + 1] = (a >= 1) ? poll_tagged(p, p.halo + a, p.epoch, p.halo_sys).y : 0;
+            hi[r + 1] = (b >= 1) ? poll_tagged(p, p.halo + b, p.epoch, p.halo_sys).y : 0;
             mn = min(mn, min(lo[r + 1], hi[r + 1]));
         }
         base = max(__reduce_min_sync(FULL_MASK, mn) - 8, 0);
@@ -189,13 +190,16 @@ __device__ __forceinline__ void run_strip16(const StripParams& p, const int s, c
             if (s > 0) {
                 const int col = cb + lane;
                 const bool need = col < ncols;
+                SpinGuard sg;
                 while (!__all_sync(FULL_MASK, !need || pre.x == p.epoch)) {
                     if (need && pre.x != p.epoch) pre = ld_tagged_gpu(tin + col + 1);
+                    if (__any_sync(FULL_MASK, sg.expired(p))) break;
                 }
                 v = pre.y;
                 if (col + 32 < ncols) pre = ld_tagged_gpu(tin + col + 33);
             }
             sin[lane] = (uint32_t)(v - base) & 0xffffu;
+            if (b == 0 && p.times != nullptr && lane == 0) { p.times[4 * s] = global_ns(); p.times[4 * s + 2] = (unsigned long long)clock64(); }
         }
         __syncwarp();
         if (cb >= 64 && cb + 31 < ncols)
@@ -234,6 +238,7 @@ __device__ __forceinline__ void run_strip16(const StripParams& p, const int s, c
         }
     }
 
+    if (p.times != nullptr && lane == 0) { p.times[4 * s + 1] = global_ns(); p.times[4 * s + 3] = (unsigned long long)clock64(); }
     // right boundary column of this lane's rows (absolute G)
     if (p.rcol != nullptr) {
 #pragma unroll
@@ -259,16 +264,7 @@ __global__ void __launch_bounds__(512) nw_strip16_kernel(const StripParams p)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     uint32_t* smem = nw_smem + warp * SMEM16_WORDS_PER_WARP;
     const int slot = blockIdx.x * nwarps + warp, nslots = gridDim.x * nwarps;
-    if (p.ack_in != nullptr) {          // do not overwrite a mailbox the consumer has not finished reading
-        if (threadIdx.x == 0) {
-            int a;
-            do {
-                asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(a) : "l"(p.ack_in) : "memory");
-                if (a < p.epoch - 2) __nanosleep(500);
-            } while (a < p.epoch - 2);
-        }
-        __syncthreads();
-    }
+    wait_mailbox_free(p);
     for (int s = slot; s < p.nstrips; s += nslots) run_strip16<R>(p, s, lane, smem);
 }
 

@@ -22,7 +22,7 @@ EXPORTS = [
     "nw_plan_create", "nw_plan_destroy", "nw_plan_upload", "nw_plan_upload_device", "nw_plan_connect",
     "nw_plan_export_mailbox", "nw_plan_import_mailbox", "nw_plan_run", "nw_plan_sync", "nw_plan_time",
     "nw_plan_timer_start", "nw_plan_timer_stop", "nw_plan_last_ms", "nw_plan_launches_per_run", "nw_plan_score", "nw_plan_last_row", "nw_plan_last_col",
-    "nw_plan_table_to_host", "nw_plan_table_device", "nw_plan_traceback", "nw_plan_strip_info", "nw_plan_strip_row",
+    "nw_plan_table_to_host", "nw_plan_table_device", "nw_plan_traceback", "nw_plan_strip_info", "nw_plan_strip_row", "nw_plan_strip_times",
     "nw_batch_create", "nw_batch_destroy", "nw_batch_upload", "nw_batch_upload_device", "nw_batch_run",
     "nw_batch_sync", "nw_batch_time", "nw_batch_scores", "nw_cuda_dpx_peak",
 ]
@@ -68,6 +68,7 @@ def lib():
             "nw_plan_table_to_host": [vp, vp], "nw_plan_table_device": [vp, C.POINTER(vp), C.POINTER(i64)],
             "nw_plan_traceback": [vp, vp, vp, ip],
             "nw_plan_strip_info": [vp, ip, ip, ip, ip, ip], "nw_plan_strip_row": [vp, C.c_int, vp],
+            "nw_plan_strip_times": [vp, vp, vp, vp],
             "nw_batch_create": [C.POINTER(vp), C.c_int, i64, i32, i32], "nw_batch_destroy": [vp],
             "nw_batch_upload": [vp, vp, vp], "nw_batch_upload_device": [vp, vp, vp], "nw_batch_run": [vp],
             "nw_batch_sync": [vp], "nw_batch_time": [vp, C.c_int, C.POINTER(C.c_float)],
@@ -297,6 +298,13 @@ class Plan:
         v = [C.c_int() for _ in range(5)]
         _ck(lib().nw_plan_strip_info(self._h, *[C.byref(x) for x in v]))
         return dict(zip(["nstrips", "strip_rows", "rows_per_lane", "warps", "ctas"], [x.value for x in v]))
+
+    def strip_times(self, cycles=False):
+        """(start_ns, end_ns[, sm_cycles]) per strip of the most recent fill (device %globaltimer / clock64)."""
+        n = self.strip_info()["nstrips"]
+        a, b, c = (np.zeros(max(n, 1), dtype=np.int64) for _ in range(3))
+        _ck(lib().nw_plan_strip_times(self._h, a.ctypes.data, b.ctypes.data, c.ctypes.data))
+        return (a[:n], b[:n], c[:n]) if cycles else (a[:n], b[:n])
 
     def strip_row(self, strip):
         out = np.empty(self.ncols + 1, dtype=np.int32)

@@ -153,6 +153,11 @@ int nw_plan_traceback(nw_plan* p, int8_t* a1, int8_t* a2, int32_t* len);
  * H values of table row  n2 - (nstrips-1-k)*strip_rows  copied to HOST (ncols of this part). */
 int nw_plan_strip_info(nw_plan* p, int* nstrips, int* strip_rows, int* rows_per_lane, int* warps, int* ctas);
 int nw_plan_strip_row(nw_plan* p, int strip, int32_t* row);
+/* Trace of the most recent fill: per strip, the device %globaltimer (ns) at which its warp had the first block of its
+ * top boundary row (i.e. when it really started) and at which it finished, and (sm_cycles, may be NULL) the SM clock
+ * cycles between the two -- cycles / ns is the SM clock the strip really ran at.  Consecutive start times give the strip
+ * start-up lag that bounds a single-pair fill; packed kernels only (zeros otherwise). */
+int nw_plan_strip_times(nw_plan* p, int64_t* start_ns, int64_t* end_ns, int64_t* sm_cycles);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Batch plans (independent pairs; shards trivially, one pair-set per GPU).

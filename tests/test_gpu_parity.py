@@ -88,16 +88,14 @@ def test_boundaries_match_golden_hashes(gpu, oracle, name, kernel_kind):
     assert oracle.fnv(row) == g["fnv_lastrow"] and oracle.fnv(col) == g["fnv_lastcol"] and sc == g["score"]
 
 
-@pytest.fixture(params=["lag2", "packed16", "packed16k2", "int32"])
+@pytest.fixture(params=["lag2", "packed16", "int32"])
 def kernel_kind(request, monkeypatch):
-    """Boundary mode has four kernels: packed s16x2 with virtual lanes two columns apart (nw_lag2.cuh, the default), one
-    column apart (nw_packed.cuh; also pass 1 of full-table mode), two columns per step (nw_packed2.cuh) and 32-bit
-    (nw_kernels.cuh; generic alphabets)."""
+    """Boundary mode has three kernels: packed s16x2 with virtual lanes two columns apart (nw_lag2.cuh, the default), one
+    column apart (nw_packed.cuh; also pass 1 of full-table mode) and 32-bit (nw_kernels.cuh; generic alphabets)."""
     if request.param == "int32":
         monkeypatch.setenv("NW_CUDA_NO_PACKED", "1")
     else:
         monkeypatch.setenv("NW_CUDA_LAG2", "1" if request.param == "lag2" else "0")
-        monkeypatch.setenv("NW_CUDA_K2", "1" if request.param == "packed16k2" else "0")
     return request.param
 
 
@@ -141,11 +139,10 @@ def test_many_random_shapes(gpu, oracle, kernel_kind):
         assert np.array_equal(row, t[-1]) and np.array_equal(col, t[:, -1]) and sc == t[-1, -1], (n1, n2, hi)
 
 
-@pytest.mark.parametrize("kind", ["lag2", "lag1", "k2"])
+@pytest.mark.parametrize("kind", ["lag2", "lag1"])
 @pytest.mark.parametrize("R", [0, 2, 4, 8, 16])
 def test_boundaries_long_rows_rebase(gpu, oracle, R, kind, monkeypatch):
     monkeypatch.setenv("NW_CUDA_LAG2", "1" if kind == "lag2" else "0")
-    monkeypatch.setenv("NW_CUDA_K2", "1" if kind == "k2" else "0")
     # wide tables make the packed kernel re-base its 16-bit lanes many times; identical prefixes make G grow fastest
     rng = np.random.default_rng(9)
     s1 = rng.integers(1, 5, size=40000, dtype=np.int8)
