@@ -22,10 +22,13 @@ namespace {
 // (src/common/driver.cpp:26-30) measures the fill and its copies, not driver start-up.
 struct NwCudaWarmup {
   NwCudaWarmup() {
-    if (nw_cuda_init(0) != NW_OK) {
-      std::fprintf(stderr, "cuda: %s\n", nw_cuda_last_error());
-      std::exit(2);
-    }
+    const char* g = std::getenv("NW_CUDA_GPUS");
+    const int ngpus = (g && *g) ? std::atoi(g) : 1;
+    for (int d = 0; d < (ngpus > 1 ? ngpus : 1); ++d)
+      if (nw_cuda_init(d) != NW_OK) {
+        std::fprintf(stderr, "cuda: %s\n", nw_cuda_last_error());
+        std::exit(2);
+      }
   }
 } nwCudaWarmup;
 }

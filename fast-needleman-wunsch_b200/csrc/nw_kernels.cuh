@@ -129,6 +129,16 @@ struct SpinGuard {
         asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p.abort_host), "r"(1) : "memory");
         return true;
     }
+    // the same for a loop that the whole warp runs in lockstep (every lane calls it in every iteration): one vote per
+    // 1024 iterations instead of one per iteration
+    __device__ __forceinline__ bool expired_warp(const StripParams& p)
+    {
+        if (((n + 1) & 1023u) != 0) {
+            ++n;
+            return false;
+        }
+        return __any_sync(FULL_MASK, expired(p));
+    }
 };
 
 // producer side of a column-strip pipeline: do not overwrite a mailbox the consumer has not finished reading
@@ -272,7 +282,7 @@ __device__ __forceinline__ void run_strip(const StripParams& p, const int s, con
             while (!__all_sync(FULL_MASK, !need || pre.x == p.epoch)) {
                 __nanosleep(100);
                 if (need && pre.x != p.epoch) pre = ld_tagged_gpu(tin + col + 1);
-                if (__any_sync(FULL_MASK, sg.expired(p))) break;
+                if (sg.expired_warp(p)) break;
             }
             sin[lane] = pre.y;
             if (col + 32 < ncols) pre = ld_tagged_gpu(tin + col + 33);

@@ -238,7 +238,7 @@ __device__ __forceinline__ void run_strip16l2(const StripParams& p, const int s,
             while (!__all_sync(FULL_MASK, !need || pre.x == want)) {
                 __nanosleep(32);
                 if (need && pre.x != want) pre = ld_tagged_gpu(a);
-                if (__any_sync(FULL_MASK, sg.expired(p))) break;
+                if (sg.expired_warp(p)) break;
 #if NW_L2_DBG & 1024
                 missed = true;
 #endif

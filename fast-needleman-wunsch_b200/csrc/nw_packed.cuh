@@ -193,7 +193,7 @@ __device__ __forceinline__ void run_strip16(const StripParams& p, const int s, c
                 SpinGuard sg;
                 while (!__all_sync(FULL_MASK, !need || pre.x == p.epoch)) {
                     if (need && pre.x != p.epoch) pre = ld_tagged_gpu(tin + col + 1);
-                    if (__any_sync(FULL_MASK, sg.expired(p))) break;
+                    if (sg.expired_warp(p)) break;
                 }
                 v = pre.y;
                 if (col + 32 < ncols) pre = ld_tagged_gpu(tin + col + 33);

@@ -490,3 +490,163 @@ def test_score_mode_rectangular(gpu, oracle):
     for n1, n2 in [(30000, 300), (300, 30000), (9000, 1), (1, 9000), (5000, 0), (0, 5000)]:
         s1, s2 = synth_pair(n1 + 2 * n2, n1, n2, 5)
         assert gpu.score(s1, s2) == oracle.score(s1, s2), (n1, n2)
+
+
+# ---- round 2: robustness of the plug-in path -------------------------------------------------------------------------------
+def test_table_rows_wider_than_the_staging_buffer(gpu, oracle, monkeypatch):
+    # a host row wider than the pinned staging buffer used to overrun it.  1 MB staging, rows of 1.2 MB.
+    monkeypatch.setenv("NW_CUDA_STAGE_MB", "1")
+    n1, n2 = 300_000, 40
+    s1, s2 = synth_pair(77, n1, n2, 5)
+    t = np.full((n2 + 1, n1 + 1), -9, dtype=np.int32)          # pageable
+    gpu.needlemanWunsch(s1, s2, t)
+    assert np.array_equal(t, oracle.fill(s1, s2))
+    with gpu.Plan(n1, n2, mode=gpu.NW_MODE_FULL, part=1, nparts=2) as _:
+        pass                                                   # (creation only: column parts deliver 2-D slices too)
+    plans = [gpu.Plan(n1, n2, mode=gpu.NW_MODE_FULL, part=k, nparts=2, rows_per_lane=4) for k in range(2)]
+    try:
+        plans[0].connect(plans[1])
+        out = np.zeros_like(t)
+        for p in plans:
+            p.upload(s1, s2)
+            p.run()
+            p.sync()
+            p.table_to_host(out)
+        assert np.array_equal(out, t)
+    finally:
+        for p in plans:
+            p.close()
+    monkeypatch.setenv("NW_CUDA_STAGE_MB", "32")
+    gpu.needlemanWunsch(s1[:100], s2, np.empty((n2 + 1, 101), dtype=np.int32))      # back to the default buffers
+
+
+def test_failing_fill_prints_to_stderr_and_exits_2(gpu):
+    # no device -> the reference's driver around our entry point prints no score and exits with status 2 (no CPU fallback)
+    import os
+    import subprocess
+    from conftest import ROOT, pair_paths
+    exe = os.path.join(ROOT, "fast-needleman-wunsch_b200", "bin", "cuda.e")
+    if not os.path.exists(exe):
+        pytest.skip("cuda.e not built (no reference tree at build time)")
+    a, b = pair_paths("smid")
+    out = subprocess.run([exe, a, b], capture_output=True, text=True, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert out.returncode == 2, (out.returncode, out.stdout, out.stderr)
+    assert "Score" not in out.stdout and out.stderr.startswith("cuda:")
+    out = subprocess.run([exe, a, b], capture_output=True, text=True, env=dict(os.environ, NW_CUDA_MODE="sideways"))
+    assert out.returncode == 2 and "Score" not in out.stdout and "NW_CUDA_MODE" in out.stderr
+
+
+def test_a_part_without_its_left_neighbour_times_out_instead_of_hanging(gpu, oracle, monkeypatch):
+    # wait loops are bounded.  Part 1 of 2 run alone never receives its halo: the fill gives up after
+    # NW_CUDA_SPIN_TIMEOUT_MS, the call fails, and the library keeps working afterwards.
+    monkeypatch.setenv("NW_CUDA_SPIN_TIMEOUT_MS", "300")
+    s1, s2 = synth_pair(5, 4000, 3000, 5)
+    with gpu.Plan(s1.size, s2.size, part=1, nparts=2, rows_per_lane=8) as p:
+        p.upload(s1, s2)
+        p.run()
+        with pytest.raises(gpu.NwCudaError, match="aborted"):
+            p.sync()
+    monkeypatch.setenv("NW_CUDA_SPIN_TIMEOUT_MS", "20000")
+    assert gpu.score(s1, s2) == oracle.score(s1, s2)
+
+
+def test_one_shot_cache_is_dropped_after_a_failure(gpu, oracle):
+    # a failed one-shot call must not leave half-advanced cached plans behind
+    s1, s2 = synth_pair(6, 3000, 2500, 5)
+    t = np.empty((s2.size + 1, s1.size + 1), dtype=np.int32)
+    gpu.needlemanWunsch(s1, s2, t)
+    with pytest.raises(gpu.NwCudaError):
+        gpu.needlemanWunsch(s1, s2, t, ngpus=64)               # more GPUs than there are
+    gpu.needlemanWunsch(s1, s2, t)
+    assert np.array_equal(t, oracle.fill(s1, s2))
+
+
+def test_strip_trace(gpu):
+    s1, s2 = synth_pair(8, 20000, 2048, 5)
+    with gpu.Plan(s1.size, s2.size, rows_per_lane=8) as p:
+        p.upload(s1, s2)
+        p.run()
+        p.sync()
+        a, b, cyc = p.strip_times(cycles=True)
+        assert len(a) == p.strip_info()["nstrips"] == 8
+        assert (b > a).all() and (np.diff(a) > 0).all() and (cyc > 0).all()      # strips start one after the other
+        mhz = cyc / (b - a) * 1e3
+        assert ((mhz > 500) & (mhz < 3000)).all()
+
+
+def test_random_stress(gpu, oracle, monkeypatch):
+    # tools/stress.py as a test: ~200 seeded random cases over every mode against the oracle
+    rng = np.random.default_rng(20260101)
+    for case in range(200):
+        kind = int(rng.integers(0, 6))
+        hi = int(rng.choice([2, 3, 5, 5, 5, 5, 9, 100]))
+        monkeypatch.setenv("NW_CUDA_LAG2", str(int(rng.integers(0, 2))))
+        if kind <= 3:
+            n1, n2 = int(rng.integers(0, 3000)), int(rng.integers(0, 3000))
+            if rng.random() < 0.15:
+                n1 = int(rng.integers(0, 40000))
+            if rng.random() < 0.15:
+                n2 = int(rng.integers(0, 15000))
+            s1 = rng.integers(1, hi, size=n1, dtype=np.int8)
+            s2 = rng.integers(1, hi, size=n2, dtype=np.int8)
+            if rng.random() < 0.3 and min(n1, n2) > 10:        # long common stretch: fastest growth of G
+                k = int(rng.integers(1, min(n1, n2)))
+                s2[:k] = s1[:k]
+            R = int(rng.choice([0, 0, 1, 2, 4, 8, 16]))
+            if hi > 5 and R == 16:
+                R = 8
+            row, col, sc, _ = oracle.boundaries(s1, s2)
+            tag = (case, kind, n1, n2, hi, R)
+            if kind == 0:
+                with gpu.Plan(n1, n2, rows_per_lane=R) as p:
+                    p.upload(s1, s2)
+                    p.run()
+                    assert np.array_equal(p.last_row(), row) and np.array_equal(p.last_col(), col) and p.score() == sc, tag
+            elif kind == 1:
+                with gpu.Plan(n1, n2, mode=gpu.NW_MODE_SCORE, rows_per_lane=R) as p:
+                    p.upload(s1, s2)
+                    p.run()
+                    assert p.score() == sc, tag
+            elif kind == 2 and (n1 + 1) * (n2 + 1) < 30_000_000:
+                monkeypatch.setenv("NW_CUDA_TILE_BLOCKS", str(int(rng.choice([2, 5, 32]))))
+                with gpu.Plan(n1, n2, mode=gpu.NW_MODE_FULL, rows_per_lane=R) as p:
+                    p.upload(s1, s2)
+                    p.run()
+                    assert np.array_equal(p.table_to_host(), oracle.fill(s1, s2)), tag
+            elif kind == 3 and n1 >= 64:
+                P = int(rng.choice([2, 3, 5]))
+                plans = [gpu.Plan(n1, n2, part=k, nparts=P, rows_per_lane=R if R else 4) for k in range(P)]
+                try:
+                    for a, b in zip(plans, plans[1:]):
+                        a.connect(b)
+                    for p in plans:
+                        p.upload(s1, s2)
+                    for p in plans:
+                        p.run()
+                        p.sync()
+                    assert plans[-1].score() == sc and np.array_equal(plans[-1].last_col(), col), tag + (P,)
+                finally:
+                    for p in plans:
+                        p.close()
+        else:
+            npairs, l1, l2 = int(rng.integers(1, 200)), int(rng.integers(0, 1500)), int(rng.integers(0, 1500))
+            S1 = rng.integers(1, hi, size=(npairs, l1), dtype=np.int8)
+            S2 = rng.integers(1, hi, size=(npairs, l2), dtype=np.int8)
+            assert np.array_equal(gpu.batch_scores(S1, S2), oracle.batch_scores(S1, S2)), (case, npairs, l1, l2, hi)
+
+
+@pytest.mark.parametrize("what", ["synthetic", "64gb"])
+def test_multi_process_ipc_pipeline(gpu, what):
+    # one process per GPU, CUDA-IPC halo mailboxes: the path `bench.py --gpus N` and the driver's SCALE run use
+    _need_gpus(gpu, 2)
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    n = min(gpu.device_count(), 8)
+    for world in sorted({2, n}):
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                              "--master-addr", "127.0.0.1", "--master-port", "29541",
+                              os.path.join(ROOT, "tests", "mgpu_worker.py"), what],
+                             capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "mgpu_worker ok" in out.stdout, (world, out.stdout[-1500:], out.stderr[-3000:])
