@@ -175,6 +175,7 @@ __device__ __forceinline__ void run_strip16l2(const StripParams& p, const int s,
 #pragma unroll
     for (int r = 0; r < R; ++r) h[r] = 0;
     if (p.halo != nullptr) {
+        wait_halo_politely(p, (s + 1) * SH - p.pad_top);
         int lo[R + 1], hi[R + 1];
         int mn = 0x7fffffff;
 #pragma unroll

@@ -122,6 +122,21 @@ __device__ __forceinline__ int2 poll_tagged(const StripParams& sp, const int2* p
     }
 }
 
+// Column-strip parts: the left neighbour stores the halo words of a strip's rows all at once, when ITS strip of the same
+// rows ends -- for most warps of a long chain milliseconds after the kernel started.  Wait for one representative word
+// (the strip's last row) with growing sleeps, one request per warp per poll, before the lanes read their own words:
+// hundreds of warps polling system-scope words at full speed slow the working warps down several times over.
+__device__ __forceinline__ void wait_halo_politely(const StripParams& p, int i_rep)
+{
+    const int2* w = p.halo + max(i_rep, 1);
+    SpinGuard sg;
+    unsigned ns = 100;
+    while ((p.halo_sys ? ld_tagged_sys(w) : ld_tagged_gpu(w)).x != p.epoch && !sg.expired(p)) {
+        __nanosleep(ns);
+        ns = min(ns * 2, 2000u);
+    }
+}
+
 template <int R>
 __device__ __forceinline__ void run_strip16(const StripParams& p, const int s, const int lane, uint32_t* smem)
 {
@@ -149,6 +164,7 @@ __device__ __forceinline__ void run_strip16(const StripParams& p, const int s, c
 #pragma unroll
     for (int r = 0; r < R; ++r) h[r] = 0;
     if (p.halo != nullptr) {
+        wait_halo_politely(p, (s + 1) * SH - p.pad_top);
         int lo[R + 1], hi[R + 1];
         int mn = 0x7fffffff;
 #pragma unroll
