@@ -20,15 +20,16 @@ struct BatchParams {
     int len1, len2;
     int nstrips, pad_top;
     int generic;
+    int w_match, w_mis, gap;   // G-form weights and the gap score (nw_kernels.cuh); default 3, 2, -1
     uint8_t code[256];      // 4-letter path: byte value -> 0..3
 };
 
 template <bool GENERIC>
-__device__ __forceinline__ uint32_t batch_col_operand(const uint8_t* s1, int c, int len1, const uint8_t* lut)
+__device__ __forceinline__ uint32_t batch_col_operand(const uint8_t* s1, int c, int len1, const uint8_t* lut, int wm, int wx)
 {
-    if (c < 0 || c >= len1) return GENERIC ? 0x100u : 0x02020202u;
+    if (c < 0 || c >= len1) return GENERIC ? 0x100u : (uint32_t)wx * 0x01010101u;
     const uint32_t v = s1[c];
-    return GENERIC ? v : 0x02020202u + (1u << (8 * lut[v]));
+    return GENERIC ? v : weight_word(lut[v], wm, wx);
 }
 
 template <int R, bool GENERIC>
@@ -65,15 +66,16 @@ __global__ void __launch_bounds__(256) nw_batch_kernel(const BatchParams p)
                 if (k >= 0) v = GENERIC ? (uint32_t)s2[k] : (0x5550u | lut[s2[k]]);
                 else v = GENERIC ? 0x200u : 0xCCCCu;
                 ro.sel[r] = v;
-                if (GENERIC) ro.wx[GENERIC ? r : 0] = (v == 0x200u) ? -1 : 2;
+                if (GENERIC) ro.wx[GENERIC ? r : 0] = (v == 0x200u) ? -1 : p.w_mis;
             }
+            ro.wm = p.w_match;
             int dprev = 0;
 #pragma unroll
             for (int r = 0; r < R; ++r) h[r] = 0;
 
-            W[lane] = GENERIC ? 0x100u : 0x02020202u;
-            W[lane + 32] = batch_col_operand<GENERIC>(s1, lane, ncols, lut);
-            uint32_t wnext = batch_col_operand<GENERIC>(s1, 32 + lane, ncols, lut);
+            W[lane] = GENERIC ? 0x100u : (uint32_t)p.w_mis * 0x01010101u;
+            W[lane + 32] = batch_col_operand<GENERIC>(s1, lane, ncols, lut, p.w_match, p.w_mis);
+            uint32_t wnext = batch_col_operand<GENERIC>(s1, 32 + lane, ncols, lut, p.w_match, p.w_mis);
             int pre = 0;
             if (s > 0 && lane < ncols) pre = scratch[lane];
             for (int b = 0; b < nblocks; ++b) {
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(256) nw_batch_kernel(const BatchParams p)
                 if (b > 0) {
                     W[lane] = W[lane + 32];
                     W[lane + 32] = wnext;
-                    wnext = batch_col_operand<GENERIC>(s1, cb + 32 + lane, ncols, lut);
+                    wnext = batch_col_operand<GENERIC>(s1, cb + 32 + lane, ncols, lut, p.w_match, p.w_mis);
                 }
                 sin[lane] = pre;
                 if (s > 0 && cb + 32 + lane < ncols) pre = scratch[cb + 32 + lane];
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(256) nw_batch_kernel(const BatchParams p)
             __syncwarp();
         }
         // lane 31 holds G[len2][len1] (or 0 when there is no interior); H = G - i - j
-        if (lane == 31) p.scores[pair] = ((ncols > 0 && p.nstrips > 0) ? h[R - 1] : 0) - p.len1 - p.len2;
+        if (lane == 31) p.scores[pair] = ((ncols > 0 && p.nstrips > 0) ? h[R - 1] : 0) + p.gap * (p.len1 + p.len2);
     }
 }
 
@@ -107,17 +109,17 @@ __global__ void __launch_bounds__(256) nw_batch_kernel(const BatchParams p)
 
 // ---- packed (s16x2) batch kernel ----------------------------------------------------------------------------------------
 // One warp per pair, the 64-virtual-lane sweep of nw_packed.cuh (two cells per register), no re-basing: the host only
-// selects this kernel when 3 * min(len1, len2) + 64 fits 15 bits, so absolute G values fit the 16-bit lanes.
+// selects this kernel when max weight * min(len1, len2) + 64 fits 15 bits, so absolute G values fit the 16-bit lanes.
 // Rows beyond one strip (64*R rows) are handled strip after strip by the same warp through a per-warp scratch row.
 #include "nw_packed.cuh"
 
 namespace nw {
 
 // profile word of column c for the packed batch kernel: all-zero (weight 0) before the first column
-__device__ __forceinline__ uint32_t batch16_col_operand(const uint8_t* s1, int c, int len1, const uint8_t* lut)
+__device__ __forceinline__ uint32_t batch16_col_operand(const uint8_t* s1, int c, int len1, const uint8_t* lut, int wm, int wx)
 {
-    if (c >= len1) return 0x02020202u;
-    return 0x02020202u + (1u << (8 * lut[s1[c]]));
+    if (c >= len1) return (uint32_t)wx * 0x01010101u;
+    return weight_word(lut[s1[c]], wm, wx);
 }
 
 template <int R>
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(128) nw_batch16_kernel(const BatchParams p)
             uint32_t dprev = 0;
 #pragma unroll
             for (int r = 0; r < R; ++r) h[r] = 0;
-            uint32_t wnext = batch16_col_operand(s1, lane, ncols, lut);
+            uint32_t wnext = batch16_col_operand(s1, lane, ncols, lut, p.w_match, p.w_mis);
             int pre = 0;
             if (s > 0 && lane < ncols) pre = scratch[lane];
             uint32_t scar = __shfl_sync(FULL_MASK, h[R - 1], src_lane);
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(128) nw_batch16_kernel(const BatchParams p)
                 const int cb = b << 5;
 #pragma unroll
                 for (int m = 0; m < 4; ++m) ring[m * RING_COPY_WORDS + ((cb + lane + m) & 127)] = wnext;
-                wnext = batch16_col_operand(s1, cb + 32 + lane, ncols, lut);
+                wnext = batch16_col_operand(s1, cb + 32 + lane, ncols, lut, p.w_match, p.w_mis);
                 sin[lane] = (uint32_t)pre & 0xffffu;
                 pre = 0;
                 if (s > 0 && cb + 32 + lane < ncols) pre = scratch[cb + 32 + lane];
@@ -195,10 +197,10 @@ __global__ void __launch_bounds__(128) nw_batch16_kernel(const BatchParams p)
             if (s + 1 == p.nstrips) {
                 // exactly one lane of one block saw column ncols-1
                 score_g = __reduce_max_sync(FULL_MASK, score_g);
-                if (lane == 0) p.scores[pair] = ((ncols > 0) ? score_g : 0) - p.len1 - p.len2;
+                if (lane == 0) p.scores[pair] = ((ncols > 0) ? score_g : 0) + p.gap * (p.len1 + p.len2);
             }
         }
-        if (p.nstrips == 0 && lane == 0) p.scores[pair] = -p.len1 - p.len2;
+        if (p.nstrips == 0 && lane == 0) p.scores[pair] = p.gap * (p.len1 + p.len2);
     }
 }
 

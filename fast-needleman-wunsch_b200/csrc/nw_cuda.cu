@@ -10,6 +10,7 @@
 #include "nw_packed.cuh"
 #include "nw_batch.cuh"
 #include "nw_lag2.cuh"
+#include "nw_ws.cuh"
 
 #include <cooperative_groups.h>
 #include <algorithm>
@@ -149,6 +150,17 @@ StripKernel strip16l2_kernel(int regs)
     }
 }
 
+StripKernel strip16ws_kernel(int regs)
+{
+    switch (regs) {
+    case 1: return nw::nw_strip16ws_kernel<1>;
+    case 2: return nw::nw_strip16ws_kernel<2>;
+    case 4: return nw::nw_strip16ws_kernel<4>;
+    case 8: return nw::nw_strip16ws_kernel<8>;
+    default: return nullptr;
+    }
+}
+
 StripKernel full16_kernel(int regs)
 {
     switch (regs) {
@@ -225,6 +237,8 @@ struct nw_plan {
     int warps = 8, ctas = 0, nstrips = 0, pad_top = 0;
     bool packed = false;  // nw_packed.cuh kernel (boundary mode, at most four distinct byte values)
     bool lag2 = false;    // nw_lag2.cuh: virtual lanes two columns apart (boundary mode; the default packed kernel)
+    bool ws = false;      // nw_ws.cuh: the lag-2 sweep with a helper warp per strip (compute warp + helper warp per scheduler)
+    int threads = 0;      // threads per CTA of the strip kernel (warps * 32, or warps * 64 with helper warps)
     bool generic = false, uploaded = false;
     size_t rsel_words = 0, brow_words = 0;
     int epoch = 0;
@@ -272,6 +286,12 @@ struct nw_plan {
     int split = 0;                   // rows of the top half
     bool swapped = false;            // score mode sweeps along the SHORTER sequence (the score is symmetric in s1, s2)
     cudaEvent_t join_ev = nullptr;
+    // scoring (nw_scoring; default = the reference's macros, src/common/needleman-wunsch.hpp:11-13)
+    int sc_match = 1, sc_mis = 0, sc_gap = -1;
+    bool local = false;              // Smith-Waterman (nw_local.cuh)
+    int w_match() const { return std::max(sc_match - 2 * sc_gap, 0); }     // G-form weights (nw_kernels.cuh)
+    int w_mis() const { return std::max(sc_mis - 2 * sc_gap, 0); }
+    int w_max() const { return std::max(w_match(), w_mis()); }
 };
 
 static int ensure_device(int device)
@@ -503,7 +523,12 @@ static int plan_pick_kernel(nw_plan* p)
     // boundary mode: the lag-2 schedule (nw_lag2.cuh); NW_CUDA_LAG2=0 selects the one-column skew of nw_packed.cuh, which
     // full-table mode always uses (its pass 2 replays tiles with the same schedule)
     p->lag2 = p->packed && p->mode == NW_MODE_BOUNDARY && env_int("NW_CUDA_LAG2", 1) != 0;
-    if (p->lag2) {
+    p->ws = p->lag2 && env_int("NW_CUDA_WS", 0) != 0 && p->warps <= 8;   // opt-in: measured slower in a chain
+    p->threads = p->warps * (p->ws ? 64 : 32);
+    if (p->ws) {
+        p->kernel = strip16ws_kernel(R / 2);
+        p->smem = sizeof(uint32_t) * nw::WS_SMEM_WORDS_PER_PAIR * (size_t)p->warps;
+    } else if (p->lag2) {
         p->kernel = strip16l2_kernel(R / 2);
         p->smem = sizeof(uint32_t) * nw::L2_SMEM_WORDS_PER_WARP * (size_t)p->warps;
     } else if (p->packed) {
@@ -566,7 +591,7 @@ static int plan_pick_kernel(nw_plan* p)
     }
     int per_sm = 0;
     {
-        const int rc1 = occupancy(p->device, (const void*)p->kernel, p->warps * 32, p->smem, &per_sm);
+        const int rc1 = occupancy(p->device, (const void*)p->kernel, p->threads, p->smem, &per_sm);
         if (rc1) return rc1;
     }
     if (per_sm < 1) return fail(NW_ERR_CUDA, "strip kernel does not fit on an SM (warps=%d)", p->warps);
@@ -671,6 +696,8 @@ static int plan_encode(nw_plan* p, const bool seen[256])
     e.generic = p->generic ? 1 : 0;
     e.packed_regs = p->packed ? p->R / 2 : 0;
     e.lag2 = p->lag2 ? 1 : 0;
+    e.w_match = p->w_match();
+    e.w_mis = p->w_mis();
     nw::nw_encode_kernel<<<64, 256, 0, p->stream>>>(e);
     CK(cudaGetLastError());
     p->uploaded = true;
@@ -813,11 +840,11 @@ static int plan_enqueue(nw_plan* p)
     int2* rcol = p->rcol_target + (long long)par * p->mpitch;
     const bool have_cells = p->ncols > 0 && p->n2 > 0;
     if (p->mode == NW_MODE_FULL && !p->streamed) {
-        nw::nw_table_row0_kernel<<<64, 256, 0, p->stream>>>(p->d_table, p->ncols, p->jstart);
+        nw::nw_table_row0_kernel<<<64, 256, 0, p->stream>>>(p->d_table, p->ncols, p->jstart, p->sc_gap);
         CK(cudaGetLastError());
         if (!have_cells && p->n2 > 0) {   // no interior column: the table is just the boundary column
             if (halo) return fail(NW_ERR_UNSUPPORTED, "full-table part without interior columns");
-            nw::nw_table_col0_kernel<<<64, 256, 0, p->stream>>>(p->d_table, p->tpitch, p->n2);
+            nw::nw_table_col0_kernel<<<64, 256, 0, p->stream>>>(p->d_table, p->tpitch, p->n2, p->sc_gap);
             CK(cudaGetLastError());
         }
     }
@@ -842,6 +869,10 @@ static int plan_enqueue(nw_plan* p)
         sp.rcol_sys = p->rcol_peer ? 1 : 0;
         sp.ack_in = (p->rcol_target != p->d_rcol_local) ? (const int*)(p->rcol_target + 2 * p->mpitch) : nullptr;
         sp.times = p->d_times;
+        sp.w_match = p->w_match();
+        sp.w_mis = p->w_mis();
+        sp.gap = p->sc_gap;
+        sp.margin = 2 * p->w_max() + 10;
         {   // bounded waits (NW_CUDA_SPIN_TIMEOUT_MS, default 20 s; 0 = wait for ever)
             const int ms = env_int("NW_CUDA_SPIN_TIMEOUT_MS", 20000);
             sp.abort_flag = ms > 0 ? g_dev[p->device].d_abort_dev : nullptr;
@@ -854,7 +885,7 @@ static int plan_enqueue(nw_plan* p)
         sp.s_begin = 0;
         sp.s_count = p->nstrips;
         void* args[] = {&sp};
-        CK(cudaLaunchCooperativeKernel((const void*)p->kernel, dim3(p->ctas), dim3(p->warps * 32), args, p->smem, p->stream));
+        CK(cudaLaunchCooperativeKernel((const void*)p->kernel, dim3(p->ctas), dim3(p->threads), args, p->smem, p->stream));
         p->last_sp = sp;
         if (p->kernel2 && !p->streamed && !env_int("NW_CUDA_DBG_SKIP_PASS2", 0)) {           // pass 2: every tile of every strip at once, table stores as 128-byte row segments
             sp.ack_in = nullptr;
@@ -868,7 +899,8 @@ static int plan_enqueue(nw_plan* p)
         const int2* rc = have_cells ? rcol : nullptr;
         nw::nw_finish_kernel<<<64, 256, 0, p->stream>>>(brow_last, rc, halo, p->ncols, p->n2, p->jstart, p->d_last_row,
                                                          p->d_last_col, p->d_score,
-                                                         p->d_mailbox ? (int*)(p->d_mailbox + 2 * p->mpitch) : nullptr, p->epoch);
+                                                         p->d_mailbox ? (int*)(p->d_mailbox + 2 * p->mpitch) : nullptr, p->epoch,
+                                                         p->sc_gap);
         CK(cudaGetLastError());
     }
     return NW_OK;
@@ -1250,7 +1282,7 @@ static int plan_stream_table_to_host(nw_plan* p, int32_t* table)
         sp.s_begin = k * p->band_strips;
         sp.s_count = std::min(p->band_strips, p->nstrips - sp.s_begin);
         sp.ack_in = nullptr;
-        if (k == 0) nw::nw_table_row0_kernel<<<64, 256, 0, p->stream>>>(buf, p->ncols, p->jstart);
+        if (k == 0) nw::nw_table_row0_kernel<<<64, 256, 0, p->stream>>>(buf, p->ncols, p->jstart, p->sc_gap);
         const long long ntasks = (long long)sp.s_count * p->ntiles;
         const int ctas = (int)std::max<long long>(1, std::min<long long>((ntasks + p->warps2 - 1) / p->warps2, p->ctas2));
         p->kernel2<<<ctas, p->warps2 * 32, p->smem2, p->stream>>>(sp);
@@ -1328,7 +1360,7 @@ extern "C" int nw_plan_traceback(nw_plan* p, int8_t* a1, int8_t* a2, int32_t* le
     CK(cudaMalloc(&d_out, 2 * cap));
     CK(cudaMalloc(&d_len, sizeof(int)));
     nw::nw_traceback_kernel<<<1, 256, 0, p->stream>>>(p->d_table, p->tpitch, p->d_s1, p->d_s2, p->n1, p->n2, d_out,
-                                                      d_out + cap, d_len);
+                                                      d_out + cap, d_len, p->sc_match, p->sc_mis, p->sc_gap);
     cudaError_t e = cudaGetLastError();
     int n = 0;
     std::vector<uint8_t> r1(cap), r2(cap);
@@ -1385,7 +1417,7 @@ extern "C" int nw_plan_strip_row(nw_plan* p, int strip, int32_t* row)
     CK(cudaSetDevice(p->device));
     const int row_i = p->n2 - (p->nstrips - 1 - strip) * 32 * p->R;
     nw::nw_strip_row_kernel<<<64, 256, 0, p->stream>>>(p->brow() + (long long)strip * p->pitch, p->ncols, row_i, p->jstart,
-                                                        p->d_tmp_row);
+                                                        p->d_tmp_row, p->sc_gap);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(row, p->d_tmp_row, sizeof(int32_t) * ((size_t)p->ncols + 1), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
@@ -1402,6 +1434,7 @@ static std::vector<const void*> all_kernels()
     std::vector<const void*> v;
     for (int regs : {1, 2, 4, 8}) {
         v.push_back((const void*)strip16l2_kernel(regs));
+        v.push_back((const void*)strip16ws_kernel(regs));
         v.push_back((const void*)strip16_kernel(regs));
         v.push_back((const void*)full16_kernel(regs));
     }
@@ -1709,6 +1742,9 @@ struct nw_batch {
     uint8_t code[256];
     BatchKernel kernel = nullptr;
     size_t smem = 0;
+    int sc_match = 1, sc_mis = 0, sc_gap = -1;     // nw_scoring (default: the reference's macros)
+    int w_match() const { return std::max(sc_match - 2 * sc_gap, 0); }
+    int w_mis() const { return std::max(sc_mis - 2 * sc_gap, 0); }
 };
 
 extern "C" int nw_batch_destroy(nw_batch* b)
@@ -1731,8 +1767,10 @@ static int batch_pick_kernel(nw_batch* b)
 {
     const DeviceState& d = g_dev[b->device];
     CK(cudaSetDevice(b->device));
-    const long long gmax = 3LL * std::min(b->len1, b->len2) + 64;
-    b->packed = !b->generic && gmax < 32000 && !env_int("NW_CUDA_NO_PACKED", 0);
+    const int wmax = std::max(b->w_match(), b->w_mis());
+    const long long gmax = (long long)wmax * std::min(b->len1, b->len2) + 64;
+    b->packed = !b->generic && gmax < 32000 && wmax <= 127 && !env_int("NW_CUDA_NO_PACKED", 0);
+    if (!b->packed && !b->generic && wmax > 127) b->generic = true;        // the PRMT paths carry weights as bytes
     int R = env_int("NW_CUDA_BATCH_R", 0);       // table rows per lane
     if (R == 0) {
         // the smallest strip that covers the pair in one pass (profiles/r01_batch_sweep.log: with the edge blocks gone,
@@ -1863,6 +1901,9 @@ static int batch_enqueue(nw_batch* b)
     bp.nstrips = b->nstrips;
     bp.pad_top = b->pad_top;
     bp.generic = b->generic ? 1 : 0;
+    bp.w_match = b->w_match();
+    bp.w_mis = b->w_mis();
+    bp.gap = b->sc_gap;
     memcpy(bp.code, b->code, 256);
     b->kernel<<<b->ctas, b->warps * 32, b->smem, b->stream>>>(bp);
     CK(cudaGetLastError());

@@ -8,6 +8,12 @@
 // -- three integer-pipe instructions, two of them Blackwell DPX (__viaddmax_s32 / max).  H = G - i - j is applied
 // only where cells leave the kernel (boundary rows/columns, table stores, the score).
 //
+// General linear-gap scoring (the reference's only "configuration" is the three macros of
+// src/common/needleman-wunsch.hpp:11-13): with match M, mismatch X and gap g the same change of variable is
+//     G[i][j] = H[i][j] - g*(i + j),   w = (M or X) - 2g,   H = G + g*(i + j),
+// so the kernels only see other weight bytes (w_match, w_mis; a negative weight is clamped to 0, which is exact: G is
+// monotone along rows and columns, so diag + w <= up whenever w <= 0) and the emitting code multiplies by g.
+//
 // Decomposition: the table is cut into horizontal STRIPS of 32*R rows.  One warp owns a strip: lane L keeps R
 // consecutive rows in registers and sweeps the columns left to right, one column per step, lane L one column behind
 // lane L-1 (so a warp advances one anti-diagonal of 32 lane-blocks per step); the bottom cell of lane L-1 reaches lane
@@ -96,6 +102,9 @@ struct StripParams {
     int* abort_flag;             // device word + mapped host word: a wait that exceeds spin_ns sets both and gives up (the
     int* abort_host;             // fill's results are then garbage and the host reports NW_ERR_CUDA) -- a failed peer must
     unsigned long long spin_ns;  // not hang us.  Waiting warps re-read only the DEVICE word (a host read costs microseconds).
+    int w_match, w_mis;          // G-form weights: max(M - 2g, 0), max(X - 2g, 0)  (default scoring: 3, 2)
+    int gap;                     // g (default -1): H = G + g*(i + j) where cells leave a kernel
+    int margin;                  // packed kernels: slack below the warp's minimum when re-basing (2 * max weight + 10)
     unsigned long long* times;   // nstrips x 4: %globaltimer (ns) when a strip has its first top-row block and when it
                                  // ends, then clock64 (SM cycles) at the same two points -- the trace behind the start-up
                                  // lag numbers and the SM clock actually seen (nw_plan_strip_times); or nullptr
@@ -162,9 +171,10 @@ template <int R, bool GENERIC>
 struct RowOperands {
     uint32_t sel[R];
     int wx[GENERIC ? R : 1];
+    int wm;
     __device__ __forceinline__ int weight(int r, uint32_t cop) const
     {
-        if (GENERIC) return (sel[r] == cop) ? 3 : wx[r];
+        if (GENERIC) return (sel[r] == cop) ? wm : wx[r];
         return (int)prmt(cop, 0x80u, sel[r]);
     }
 };
@@ -173,7 +183,7 @@ template <int R, bool GENERIC, bool FULL, bool PRED>
 __device__ __forceinline__ void sweep32(int (&h)[R], int& dprev, const RowOperands<R, GENERIC>& ro,
                                         const uint32_t* __restrict__ Wl, const int* __restrict__ sin, int* sout,
                                         const int lane, const int cb, const int ncols,
-                                        int32_t* const (&trow)[FULL ? R : 1], const int (&hoff)[FULL ? R : 1])
+                                        int32_t* const (&trow)[FULL ? R : 1], const int (&hoff)[FULL ? R : 1], const int gap = -1)
 {
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
@@ -182,6 +192,7 @@ __device__ __forceinline__ void sweep32(int (&h)[R], int& dprev, const RowOperan
         if (lane == 0) up = sin[k];
         const int col = cb + k - lane;
         if (!PRED || (col >= 0 && col < ncols)) {
+            const int gcol = FULL ? gap * col : 0;
             int diag = dprev;
             dprev = up;
 #pragma unroll
@@ -191,7 +202,7 @@ __device__ __forceinline__ void sweep32(int (&h)[R], int& dprev, const RowOperan
                 diag = h[r];
                 up = max(t, up);                               // ... , G[i-1][j])
                 h[r] = up;
-                if (FULL) trow[r][col + 1] = up - hoff[r] - col;   // H = G - i - j
+                if (FULL) trow[r][col + 1] = up + hoff[r] + gcol;   // H = G + g*(i + j)
             }
         }
         if (lane == 31) sout[k] = h[R - 1];
@@ -212,8 +223,9 @@ __device__ __forceinline__ void run_strip(const StripParams& p, const int s, con
     for (int r = 0; r < R; ++r) {
         const uint32_t v = p.rsel[q0 + r];
         ro.sel[r] = v;
-        if (GENERIC) ro.wx[r] = (v == 0x200u) ? -1 : 2;
+        if (GENERIC) ro.wx[r] = (v == 0x200u) ? -1 : p.w_mis;
     }
+    ro.wm = p.w_match;
 
     // left boundary column (G form): zero for a whole table, the neighbour's right column for a column strip
     int h[R];
@@ -245,8 +257,8 @@ __device__ __forceinline__ void run_strip(const StripParams& p, const int s, con
         for (int r = 0; r < R; ++r) {
             const int i = i0 + 1 + r;
             trow[FULL ? r : 0] = (i >= 1) ? p.table + (long long)i * p.tpitch : p.dump;
-            hoff[FULL ? r : 0] = i + p.jstart + 1;     // H = G - i - (jstart + col + 1)
-            trow[FULL ? r : 0][0] = h[r] - i - p.jstart;   // left boundary column (serial.cpp:17 / mpi-vert.cpp:57-59)
+            hoff[FULL ? r : 0] = p.gap * (i + p.jstart + 1);     // H = G + g*(i + jstart + col + 1)
+            trow[FULL ? r : 0][0] = h[r] + p.gap * (i + p.jstart);   // left boundary column (serial.cpp:17 / mpi-vert.cpp:57-59)
         }
     }
 
@@ -289,9 +301,9 @@ __device__ __forceinline__ void run_strip(const StripParams& p, const int s, con
         }
         __syncwarp();
         if (cb >= 31 && cb + 31 < ncols)
-            sweep32<R, GENERIC, FULL, false>(h, dprev, ro, Wl, sin, sout, lane, cb, ncols, trow, hoff);
+            sweep32<R, GENERIC, FULL, false>(h, dprev, ro, Wl, sin, sout, lane, cb, ncols, trow, hoff, p.gap);
         else
-            sweep32<R, GENERIC, FULL, true>(h, dprev, ro, Wl, sin, sout, lane, cb, ncols, trow, hoff);
+            sweep32<R, GENERIC, FULL, true>(h, dprev, ro, Wl, sin, sout, lane, cb, ncols, trow, hoff, p.gap);
         __syncwarp();
         const int oc = cb - 31 + lane;               // column finished by lane 31 at step k = lane of this block
         const int ov = sout[lane];
@@ -349,8 +361,15 @@ struct EncodeParams {
     int generic;
     int packed_regs;        // 0: 32-bit kernels; R > 0: packed kernel with R registers per lane (strip = 64*R rows)
     int lag2;               // packed lag-2 kernel (nw_lag2.cuh): the roles of row and column operands are swapped
+    int w_match, w_mis;     // G-form weights (default 3, 2); the 4-letter paths need 0 <= w <= 127
     uint8_t code[256];      // 4-letter path: byte value -> 0..3
 };
+
+// profile word of a letter: byte b = weight of (this letter, letter with code b)
+__device__ __forceinline__ uint32_t weight_word(uint32_t code, int w_match, int w_mis)
+{
+    return (uint32_t)w_mis * 0x01010101u + ((uint32_t)(w_match - w_mis) << (8 * code));
+}
 
 __global__ void nw_encode_kernel(const EncodeParams e)
 {
@@ -358,7 +377,7 @@ __global__ void nw_encode_kernel(const EncodeParams e)
     for (int x = tid; x < e.ncols + WQ_PAD + WQ_PADR && !(e.packed_regs > 0 && e.lag2); x += nth) {
         const int c = x - WQ_PAD;
         uint32_t v;
-        if (c >= 0 && c < e.ncols) v = e.generic ? (uint32_t)e.s1[c] : 0x02020202u + (1u << (8 * e.code[e.s1[c]]));
+        if (c >= 0 && c < e.ncols) v = e.generic ? (uint32_t)e.s1[c] : weight_word(e.code[e.s1[c]], e.w_match, e.w_mis);
         else v = e.generic ? 0x100u : 0u;      // weight 0: a virtual column repeats its left neighbour (nw_lag2.cuh)
         e.wq_base[x] = v;
     }
@@ -377,8 +396,8 @@ __global__ void nw_encode_kernel(const EncodeParams e)
         for (int x = tid; x < e.nrows_padded / 2; x += nth) {
             const int s = x / (32 * R), rem = x - s * 32 * R, L = rem / R, r = rem - L * R;
             const int klo = s * 64 * R + L * R + r - e.pad_top, khi = klo + 32 * R;
-            e.rsel[2 * x] = (klo >= 0) ? 0x02020202u + (1u << (8 * e.code[e.s2[klo]])) : 0u;
-            e.rsel[2 * x + 1] = (khi >= 0) ? 0x02020202u + (1u << (8 * e.code[e.s2[khi]])) : 0u;
+            e.rsel[2 * x] = (klo >= 0) ? weight_word(e.code[e.s2[klo]], e.w_match, e.w_mis) : 0u;
+            e.rsel[2 * x + 1] = (khi >= 0) ? weight_word(e.code[e.s2[khi]], e.w_match, e.w_mis) : 0u;
         }
         return;
     }
@@ -407,10 +426,10 @@ __global__ void nw_encode_kernel(const EncodeParams e)
 
 // first row of a materialised table (reference: src/serial/serial.cpp:16, mpi-vert.cpp:20); the first column is
 // written by the strip kernel itself because in a pipeline it is the halo, which arrives while the kernel runs.
-__global__ void nw_table_row0_kernel(int32_t* table, int ncols, int jstart)
+__global__ void nw_table_row0_kernel(int32_t* table, int ncols, int jstart, int gap)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    for (int j = tid; j <= ncols; j += nth) table[j] = -(jstart + j);
+    for (int j = tid; j <= ncols; j += nth) table[j] = gap * (jstart + j);
 }
 
 // boundary outputs in H form: last_row[j] = H[n2][jstart+j], last_col[i] = H[i][jstart+ncols].
@@ -418,7 +437,7 @@ __global__ void nw_table_row0_kernel(int32_t* table, int ncols, int jstart)
 // its boundary column only);  rcol == nullptr likewise: the last column is the left boundary (the halo, or H[i][0] = -i).
 __global__ void nw_finish_kernel(const int2* brow_last, const int2* rcol, const int2* halo, int ncols, int n2,
                                  int jstart, int32_t* last_row, int32_t* last_col, int32_t* score, int* ack_out,
-                                 int epoch)
+                                 int epoch, int gap)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const int jend = jstart + ncols;
@@ -426,7 +445,7 @@ __global__ void nw_finish_kernel(const int2* brow_last, const int2* rcol, const 
         int g = 0;                                           // G of the init row / init column
         if (brow_last != nullptr) g = brow_last[j].y;
         else if (n2 > 0 && halo != nullptr) g = halo[n2].y;  // ncols == 0, j == 0
-        last_row[j] = g - n2 - (jstart + j);
+        last_row[j] = g + gap * (n2 + jstart + j);
     }
     for (int i = tid; i <= n2; i += nth) {
         int g = 0;
@@ -434,7 +453,7 @@ __global__ void nw_finish_kernel(const int2* brow_last, const int2* rcol, const 
             if (rcol != nullptr) g = rcol[i].y;
             else if (halo != nullptr) g = halo[i].y;
         }
-        last_col[i] = g - i - jend;
+        last_col[i] = g + gap * (i + jend);
     }
     if (tid == 0) {
         int g = 0;
@@ -442,7 +461,7 @@ __global__ void nw_finish_kernel(const int2* brow_last, const int2* rcol, const 
             if (rcol != nullptr) g = rcol[n2].y;
             else if (halo != nullptr) g = halo[n2].y;
         }
-        *score = g - n2 - jend;
+        *score = g + gap * (n2 + jend);
     }
     // the halo mailbox of this epoch has been consumed: let the producer (which polls this word, over NVLink when it
     // sits on another GPU) reuse it.  Stream order puts this kernel after the strip kernel.
@@ -477,17 +496,17 @@ __global__ void __launch_bounds__(256) nw_bidir_combine_kernel(const int32_t* __
 }
 
 // strip boundary row k in H form (checkpoint rows kept in HBM)
-__global__ void nw_strip_row_kernel(const int2* brow, int ncols, int row_i, int jstart, int32_t* out)
+__global__ void nw_strip_row_kernel(const int2* brow, int ncols, int row_i, int jstart, int32_t* out, int gap)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    for (int j = tid; j <= ncols; j += nth) out[j] = brow[j].y - row_i - (jstart + j);
+    for (int j = tid; j <= ncols; j += nth) out[j] = brow[j].y + gap * (row_i + jstart + j);
 }
 
 // table column 0 of a part that has no interior column (n1 == 0): H[i][0] = -i (src/serial/serial.cpp:17)
-__global__ void nw_table_col0_kernel(int32_t* table, long long tpitch, int n2)
+__global__ void nw_table_col0_kernel(int32_t* table, long long tpitch, int n2, int gap)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    for (int i = tid + 1; i <= n2; i += nth) table[(long long)i * tpitch] = -i;
+    for (int i = tid + 1; i <= n2; i += nth) table[(long long)i * tpitch] = gap * i;
 }
 
 // presence bitmap over a large byte array (batch inputs), 16 bytes per load where aligned
@@ -530,7 +549,8 @@ __global__ void nw_presence_kernel64(const uint8_t* s, long long n, uint32_t* bi
 constexpr int TB_W = 64;
 __global__ void __launch_bounds__(256) nw_traceback_kernel(const int32_t* __restrict__ table, long long tpitch,
                                                            const uint8_t* __restrict__ s1, const uint8_t* __restrict__ s2,
-                                                           int n1, int n2, uint8_t* out1, uint8_t* out2, int* out_len)
+                                                           int n1, int n2, uint8_t* out1, uint8_t* out2, int* out_len,
+                                                           int sc_match, int sc_mis, int sc_gap)
 {
     __shared__ int win[TB_W][TB_W + 1];
     __shared__ uint8_t c1[TB_W], c2[TB_W];
@@ -565,8 +585,8 @@ __global__ void __launch_bounds__(256) nw_traceback_kernel(const int32_t* __rest
                 else {
                     if (a == 0 || b == 0) break;               // neighbours outside: re-stage the window
                     const int h = win[a][b];
-                    if (h == win[a - 1][b - 1] + (c1[b] == c2[a] ? 1 : 0)) move = 0;
-                    else if (h == win[a - 1][b] - 1) move = 1;
+                    if (h == win[a - 1][b - 1] + (c1[b] == c2[a] ? sc_match : sc_mis)) move = 0;
+                    else if (h == win[a - 1][b] + sc_gap) move = 1;
                     else move = 2;
                 }
                 if (move == 2 && gi == 0 && b == 0) break;     // need the previous window for the sequence byte

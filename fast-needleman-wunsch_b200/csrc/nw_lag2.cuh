@@ -185,7 +185,7 @@ __device__ __forceinline__ void run_strip16l2(const StripParams& p, const int s,
             hi[r + 1] = (b >= 1) ? poll_tagged(p, p.halo + b, p.epoch, p.halo_sys).y : 0;
             mn = min(mn, min(lo[r + 1], hi[r + 1]));
         }
-        base = max(__reduce_min_sync(FULL_MASK, mn) - 16, 0);
+        base = max(__reduce_min_sync(FULL_MASK, mn) - p.margin, 0);
         dprev = ((uint32_t)(lo[0] - base) & 0xffffu) | ((uint32_t)(hi[0] - base) << 16);
 #pragma unroll
         for (int r = 0; r < R; ++r) h[r] = ((uint32_t)(lo[r + 1] - base) & 0xffffu) | ((uint32_t)(hi[r + 1] - base) << 16);
@@ -288,7 +288,7 @@ __device__ __forceinline__ void run_strip16l2(const StripParams& p, const int s,
             for (int r = 0; r < R; ++r) mm = __vmins2(mm, h[r]);
             int m = min((int)(short)(mm & 0xffffu), (int)mm >> 16);
             m = __reduce_min_sync(FULL_MASK, m);
-            const int D = m - 16;                        // in-flight shuffles are up to two steps (6) older than h
+            const int D = m - p.margin;                       // in-flight shuffles are up to two steps (6) older than h
             if (D > 0) {
                 const uint32_t Dp = (uint32_t)D * 0x10001u;       // every half is >= D: no borrow between halves
 #pragma unroll

@@ -174,7 +174,7 @@ __device__ __forceinline__ void run_strip16(const StripParams& p, const int s, c
             hi[r + 1] = (b >= 1) ? poll_tagged(p, p.halo + b, p.epoch, p.halo_sys).y : 0;
             mn = min(mn, min(lo[r + 1], hi[r + 1]));
         }
-        base = max(__reduce_min_sync(FULL_MASK, mn) - 8, 0);
+        base = max(__reduce_min_sync(FULL_MASK, mn) - p.margin, 0);
         dprev = ((uint32_t)(lo[0] - base) & 0xffffu) | ((uint32_t)(hi[0] - base) << 16);
 #pragma unroll
         for (int r = 0; r < R; ++r) h[r] = ((uint32_t)(lo[r + 1] - base) & 0xffffu) | ((uint32_t)(hi[r + 1] - base) << 16);
@@ -233,7 +233,7 @@ __device__ __forceinline__ void run_strip16(const StripParams& p, const int s, c
             for (int r = 0; r < R; ++r) mm = __vmins2(mm, h[r]);
             int m = min((int)(short)(mm & 0xffffu), (int)mm >> 16);
             m = __reduce_min_sync(FULL_MASK, m);
-            const int D = m - 8;
+            const int D = m - p.margin;
             if (D > 0) {
                 const uint32_t Dp = (uint32_t)D * 0x10001u;       // every half is >= D: no borrow between halves
 #pragma unroll
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(256) nw_full16_kernel(const StripParams p)
                     hi[r + 1] = (b >= 1) ? p.halo[b].y : 0;
                     mn = min(mn, min(lo[r + 1], hi[r + 1]));
                 }
-                base = max(__reduce_min_sync(FULL_MASK, mn) - 8, 0);
+                base = max(__reduce_min_sync(FULL_MASK, mn) - p.margin, 0);
                 dprev = ((uint32_t)(lo[0] - base) & 0xffffu) | ((uint32_t)(hi[0] - base) << 16);
 #pragma unroll
                 for (int r = 0; r < R; ++r)
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(256) nw_full16_kernel(const StripParams p)
                 for (int r = 0; r < R; ++r) mm = __vmins2(mm, h[r]);
                 int mv = min((int)(short)(mm & 0xffffu), (int)mm >> 16);
                 mv = __reduce_min_sync(FULL_MASK, mv);
-                const int D = mv - 8;
+                const int D = mv - p.margin;
                 if (D > 0) {
                     const uint32_t Dp = (uint32_t)D * 0x10001u;
 #pragma unroll
