@@ -34,7 +34,10 @@ struct NwCudaWarmup {
 }
 
 void needlemanWunsch(dnaArray s1, dnaArray s2, int* t) {
-  if (nw_cuda_fill(s1.dna, s1.size, s2.dna, s2.size, t) != NW_OK) {
+  // the scoring is whatever needleman-wunsch.hpp defines (MATCH / MISMATCH / GAP, src/common/needleman-wunsch.hpp:11-13): a
+  // maintainer who edits those macros gets the same change here; mode and GPU count come from the environment (-1, 0)
+  const nw_scoring scoring = {MATCH, MISMATCH, GAP, 0, {0, 0, 0, 0}};
+  if (nw_cuda_fill_scored(s1.dna, s1.size, s2.dna, s2.size, t, -1, 0, &scoring) != NW_OK) {
     std::fprintf(stderr, "cuda: %s\n", nw_cuda_last_error());
     std::exit(2);
   }

@@ -11,6 +11,7 @@
 #include "nw_batch.cuh"
 #include "nw_lag2.cuh"
 #include "nw_ws.cuh"
+#include "nw_local.cuh"
 
 #include <cooperative_groups.h>
 #include <algorithm>
@@ -161,6 +162,17 @@ StripKernel strip16ws_kernel(int regs)
     }
 }
 
+StripKernel local_kernel(int R, bool full)
+{
+    switch (R) {
+    case 1: return full ? nw::nw_local_kernel<1, true> : nw::nw_local_kernel<1, false>;
+    case 2: return full ? nw::nw_local_kernel<2, true> : nw::nw_local_kernel<2, false>;
+    case 4: return full ? nw::nw_local_kernel<4, true> : nw::nw_local_kernel<4, false>;
+    case 8: return full ? nw::nw_local_kernel<8, true> : nw::nw_local_kernel<8, false>;
+    default: return nullptr;
+    }
+}
+
 StripKernel full16_kernel(int regs)
 {
     switch (regs) {
@@ -222,6 +234,29 @@ void bitmap_to_seen(const uint32_t bm[8], bool seen[256])
     for (int v = 0; v < 256; ++v) seen[v] = (bm[v >> 5] >> (v & 31)) & 1u;
 }
 
+// validated copy of an nw_scoring (NULL = the reference's macros, src/common/needleman-wunsch.hpp:11-13)
+struct Scoring {
+    int match = 1, mismatch = 0, gap = -1, local = 0;
+    bool operator==(const Scoring& o) const { return match == o.match && mismatch == o.mismatch && gap == o.gap && local == o.local; }
+};
+int parse_scoring(const nw_scoring* in, int32_t n1, int32_t n2, Scoring* out)
+{
+    Scoring sc;
+    if (in) {
+        for (int k = 0; k < 4; ++k)
+            if (in->reserved[k] != 0) return fail(NW_ERR_ARG, "nw_scoring.reserved must be zero");
+        if (in->local != 0 && in->local != 1) return fail(NW_ERR_ARG, "nw_scoring.local must be 0 or 1 (got %d)", in->local);
+        sc.match = in->match; sc.mismatch = in->mismatch; sc.gap = in->gap; sc.local = in->local;
+    }
+    if (sc.local && sc.gap > 0) return fail(NW_ERR_ARG, "local alignment needs gap <= 0 (got %d)", sc.gap);
+    long long a = std::max({std::llabs((long long)sc.match), std::llabs((long long)sc.mismatch), std::llabs((long long)sc.gap)});
+    a = std::max(a, 2 * std::llabs((long long)sc.gap) + std::max(std::llabs((long long)sc.match), std::llabs((long long)sc.mismatch)));
+    if (a * ((long long)n1 + n2 + 2) >= (1LL << 30))
+        return fail(NW_ERR_ARG, "scores (%d, %d, %d) overflow int32 on a %d x %d table", sc.match, sc.mismatch, sc.gap, n1, n2);
+    *out = sc;
+    return NW_OK;
+}
+
 }  // namespace
 
 // =====================================================================================================================
@@ -253,6 +288,8 @@ struct nw_plan {
     unsigned long long* d_times = nullptr;     // nstrips x 2 %globaltimer stamps of the most recent fill
     size_t times_strips = 0;
     uint8_t* d_rev = nullptr;                  // score mode, bottom half: staging of the sequences before reversal
+    int4* d_local_best = nullptr;              // local alignment: best cell per strip
+    size_t local_best_n = 0;
 
     int2* d_mailbox = nullptr;       // 2 x mpitch tagged words: halo of parts > 0 (double-buffered by epoch parity)
     int2* d_rcol_local = nullptr;    // 2 x mpitch: right column when nobody is connected on the right
@@ -418,7 +455,8 @@ extern "C" int nw_plan_destroy(nw_plan* p)
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->ipc_mailbox) cudaIpcCloseMemHandle(p->ipc_mailbox);
     void* bufs[] = {p->d_s1, p->d_s2, p->d_wq, p->d_rsel, p->d_bitmap, p->d_brow, p->d_rcol_local, p->d_table,
-                    p->d_dump, p->d_snap, p->d_last_row, p->d_last_col, p->d_score, p->d_tmp_row, p->d_rev, p->d_times};
+                    p->d_dump, p->d_snap, p->d_last_row, p->d_last_col, p->d_score, p->d_tmp_row, p->d_rev, p->d_times,
+                    p->d_local_best};
     for (void* b : bufs)
         if (b) cudaFreeAsync(b, p->stream ? p->stream : (cudaStream_t)0);      // back into the device's pool
     if (p->stream) cudaStreamSynchronize(p->stream);
@@ -489,8 +527,10 @@ static int plan_pick_kernel(nw_plan* p)
 {
     const DeviceState& d = g_dev[p->device];
     CK(cudaSetDevice(p->device));
-    p->packed = !p->generic && !env_int("NW_CUDA_NO_PACKED", 0) && p->R_req != 1 &&
-                (p->mode == NW_MODE_BOUNDARY || !env_int("NW_CUDA_NO_PACKED_FULL", 0));
+    // packed s16x2 kernels: four letters, small weights (the 16-bit window and its re-basing margin are sized for them),
+    // and -- full-table mode, whose pass 2 emits H = G - i - j -- the reference's gap of -1
+    p->packed = !p->generic && !p->local && !env_int("NW_CUDA_NO_PACKED", 0) && p->R_req != 1 && p->w_max() <= 16 &&
+                (p->mode == NW_MODE_BOUNDARY || (!env_int("NW_CUDA_NO_PACKED_FULL", 0) && p->sc_gap == -1));
     int R = p->R_req;
     if (R == 0) R = p->packed ? choose_rows_per_lane_packed(p->n2, p->ncols, d.sm_count)
                               : choose_rows_per_lane(p->n2, p->ncols, d.sm_count);
@@ -534,6 +574,15 @@ static int plan_pick_kernel(nw_plan* p)
     } else if (p->packed) {
         p->kernel = strip16_kernel(R / 2);
         p->smem = sizeof(uint32_t) * nw::SMEM16_WORDS_PER_WARP * (size_t)p->warps;
+    } else if (p->local) {
+        p->kernel = local_kernel(R, p->mode == NW_MODE_FULL);
+        p->smem = sizeof(uint32_t) * nw::SMEM_WORDS_PER_WARP * (size_t)p->warps;
+        if ((size_t)std::max(p->nstrips, 1) > p->local_best_n) {
+            if (p->d_local_best) CK(cudaFreeAsync(p->d_local_best, p->stream));
+            p->d_local_best = nullptr;
+            p->local_best_n = (size_t)std::max(p->nstrips, 1);
+            CK(dev_alloc(p->device, p->stream, &p->d_local_best, sizeof(int4) * p->local_best_n));
+        }
     } else {
         p->kernel = strip_kernel(R, p->generic, p->mode == NW_MODE_FULL);
         p->smem = sizeof(uint32_t) * nw::SMEM_WORDS_PER_WARP * (size_t)p->warps;
@@ -609,20 +658,35 @@ static int plan_pick_kernel(nw_plan* p)
 }
 
 static int plan_create_internal(nw_plan** out, int device, int32_t n1, int32_t n2, int mode, int part, int nparts,
-                                const nw_tuning* tuning, bool want_streamed);
+                                const nw_tuning* tuning, bool want_streamed, const Scoring& sc);
 
 extern "C" int nw_plan_create(nw_plan** out, int device, int32_t n1, int32_t n2, int mode, int part, int nparts,
                               const nw_tuning* tuning)
 {
-    return plan_create_internal(out, device, n1, n2, mode, part, nparts, tuning, false);
+    return plan_create_internal(out, device, n1, n2, mode, part, nparts, tuning, false, Scoring());
+}
+
+extern "C" int nw_plan_create_scored(nw_plan** out, int device, int32_t n1, int32_t n2, int mode, int part, int nparts,
+                                     const nw_tuning* tuning, const nw_scoring* scoring)
+{
+    if (out) *out = nullptr;
+    if (n1 < 0 || n2 < 0) return fail(NW_ERR_ARG, "negative sequence length (n1=%d, n2=%d)", n1, n2);
+    Scoring sc;
+    const int rc = parse_scoring(scoring, n1, n2, &sc);
+    if (rc) return rc;
+    return plan_create_internal(out, device, n1, n2, mode, part, nparts, tuning, false, sc);
 }
 
 static int plan_create_internal(nw_plan** out, int device, int32_t n1, int32_t n2, int mode, int part, int nparts,
-                                const nw_tuning* tuning, bool want_streamed)
+                                const nw_tuning* tuning, bool want_streamed, const Scoring& sc)
 {
     if (!out) return fail(NW_ERR_ARG, "out is NULL");
     *out = nullptr;
     if (n1 < 0 || n2 < 0) return fail(NW_ERR_ARG, "negative sequence length (n1=%d, n2=%d)", n1, n2);
+    if (sc.local) {
+        if (nparts != 1 || part != 0) return fail(NW_ERR_UNSUPPORTED, "local alignment is a single-device mode");
+        if (mode == NW_MODE_SCORE) mode = NW_MODE_BOUNDARY;      // the best cell can be anywhere: no meeting in the middle
+    }
     if (mode == NW_MODE_SCORE) {
         if (nparts != 1 || part != 0) return fail(NW_ERR_UNSUPPORTED, "score mode is a single-device mode");
         int rc0 = ensure_device(device);
@@ -633,9 +697,10 @@ static int plan_create_internal(nw_plan** out, int device, int32_t n1, int32_t n
         q->swapped = n1 > n2 && !env_int("NW_CUDA_NO_SWAP", 0);
         if (q->swapped) std::swap(n1, n2);
         q->device = device; q->n1 = n1; q->n2 = n2; q->mode = mode;
+        q->sc_match = sc.match; q->sc_mis = sc.mismatch; q->sc_gap = sc.gap;
         q->split = n2 / 2;
-        rc0 = plan_create_internal(&q->sub[0], device, n1, q->split, NW_MODE_BOUNDARY, 0, 1, tuning, false);
-        if (rc0 == NW_OK) rc0 = plan_create_internal(&q->sub[1], device, n1, n2 - q->split, NW_MODE_BOUNDARY, 0, 1, tuning, false);
+        rc0 = plan_create_internal(&q->sub[0], device, n1, q->split, NW_MODE_BOUNDARY, 0, 1, tuning, false, sc);
+        if (rc0 == NW_OK) rc0 = plan_create_internal(&q->sub[1], device, n1, n2 - q->split, NW_MODE_BOUNDARY, 0, 1, tuning, false, sc);
         if (rc0 == NW_OK && cudaEventCreateWithFlags(&q->join_ev, cudaEventDisableTiming) != cudaSuccess)
             rc0 = fail(NW_ERR_CUDA, "cudaEventCreate failed");
         if (rc0 == NW_OK && dev_alloc(device, q->sub[0]->stream, &q->d_score, 64) != cudaSuccess)
@@ -666,6 +731,7 @@ static int plan_create_internal(nw_plan** out, int device, int32_t n1, int32_t n
     p->mode = mode;
     p->part = part;
     p->nparts = nparts;
+    p->sc_match = sc.match; p->sc_mis = sc.mismatch; p->sc_gap = sc.gap; p->local = sc.local != 0;
     p->want_streamed = want_streamed;
     partition(n1, nparts, part, &p->jstart, &p->ncols);
     rc = plan_alloc(p, tuning);
@@ -682,7 +748,8 @@ static int plan_encode(nw_plan* p, const bool seen[256])
 {
     nw::EncodeParams e;
     p->generic = !build_code(seen, e.code);
-    if (env_int("NW_CUDA_GENERIC", 0)) p->generic = true;
+    // the four-letter paths carry weights as PRMT bytes; the local kernel compares raw bytes
+    if (env_int("NW_CUDA_GENERIC", 0) || p->local || p->w_max() > 127) p->generic = true;
     int rc = plan_pick_kernel(p);
     if (rc) return rc;
     e.s1 = p->d_s1;
@@ -840,11 +907,12 @@ static int plan_enqueue(nw_plan* p)
     int2* rcol = p->rcol_target + (long long)par * p->mpitch;
     const bool have_cells = p->ncols > 0 && p->n2 > 0;
     if (p->mode == NW_MODE_FULL && !p->streamed) {
-        nw::nw_table_row0_kernel<<<64, 256, 0, p->stream>>>(p->d_table, p->ncols, p->jstart, p->sc_gap);
+        const int bgap = p->local ? 0 : p->sc_gap;      // local alignment: zero first row and column
+        nw::nw_table_row0_kernel<<<64, 256, 0, p->stream>>>(p->d_table, p->ncols, p->jstart, bgap);
         CK(cudaGetLastError());
         if (!have_cells && p->n2 > 0) {   // no interior column: the table is just the boundary column
             if (halo) return fail(NW_ERR_UNSUPPORTED, "full-table part without interior columns");
-            nw::nw_table_col0_kernel<<<64, 256, 0, p->stream>>>(p->d_table, p->tpitch, p->n2, p->sc_gap);
+            nw::nw_table_col0_kernel<<<64, 256, 0, p->stream>>>(p->d_table, p->tpitch, p->n2, bgap);
             CK(cudaGetLastError());
         }
     }
@@ -869,8 +937,9 @@ static int plan_enqueue(nw_plan* p)
         sp.rcol_sys = p->rcol_peer ? 1 : 0;
         sp.ack_in = (p->rcol_target != p->d_rcol_local) ? (const int*)(p->rcol_target + 2 * p->mpitch) : nullptr;
         sp.times = p->d_times;
-        sp.w_match = p->w_match();
-        sp.w_mis = p->w_mis();
+        sp.w_match = p->local ? p->sc_match : p->w_match();      // (the local kernel works in H form with the plain scores)
+        sp.w_mis = p->local ? p->sc_mis : p->w_mis();
+        sp.local_best = p->d_local_best;
         sp.gap = p->sc_gap;
         sp.margin = 2 * p->w_max() + 10;
         {   // bounded waits (NW_CUDA_SPIN_TIMEOUT_MS, default 20 s; 0 = wait for ever)
@@ -893,7 +962,10 @@ static int plan_enqueue(nw_plan* p)
             CK(cudaGetLastError());
         }
     }
-    {
+    if (p->local) {
+        nw::nw_local_finish_kernel<<<1, 32, 0, p->stream>>>(p->d_local_best, have_cells ? p->nstrips : 0, p->d_score);
+        CK(cudaGetLastError());
+    } else {
         const int2* brow_last = (p->n2 > 0 && have_cells) ? p->brow() + (long long)(p->nstrips - 1) * p->pitch : nullptr;
         // n2 > 0 but no interior column: the last row is the single boundary cell; handled through rcol/halo == nullptr
         const int2* rc = have_cells ? rcol : nullptr;
@@ -1075,9 +1147,31 @@ extern "C" int nw_plan_score(nw_plan* p, int32_t* score)
     return check_abort(p->device);
 }
 
+// the reported cell: (n2, n1) for global alignment, the best cell for local alignment
+extern "C" int nw_plan_best(nw_plan* p, int32_t* score, int32_t* end_i, int32_t* end_j)
+{
+    if (!p) return fail(NW_ERR_ARG, "bad argument");
+    if (p->epoch == 0) return fail(NW_ERR_STATE, "no fill has been run");
+    CK(cudaSetDevice(p->device));
+    cudaStream_t st = (p->mode == NW_MODE_SCORE) ? p->sub[0]->stream : p->stream;
+    int32_t v[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(v, p->d_score, sizeof(int32_t) * (p->local ? 3 : 1), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (!p->local) {
+        const bool sw = p->mode == NW_MODE_SCORE && p->swapped;      // a score plan may hold the sequences swapped
+        v[1] = sw ? p->n1 : p->n2;
+        v[2] = sw ? p->n2 : p->n1;
+    }
+    if (score) *score = v[0];
+    if (end_i) *end_i = v[1];
+    if (end_j) *end_j = v[2];
+    return check_abort(p->device);
+}
+
 extern "C" int nw_plan_last_row(nw_plan* p, int32_t* last_row)
 {
     if (!p || !last_row) return fail(NW_ERR_ARG, "bad argument");
+    if (p->local) return fail(NW_ERR_UNSUPPORTED, "a local-alignment plan reports its best cell (nw_plan_best), not boundaries");
     if (p->mode == NW_MODE_SCORE) return fail(NW_ERR_STATE, "a score-mode plan only has a score");
     if (p->epoch == 0) return fail(NW_ERR_STATE, "no fill has been run");
     CK(cudaSetDevice(p->device));
@@ -1089,6 +1183,7 @@ extern "C" int nw_plan_last_row(nw_plan* p, int32_t* last_row)
 extern "C" int nw_plan_last_col(nw_plan* p, int32_t* last_col)
 {
     if (!p || !last_col) return fail(NW_ERR_ARG, "bad argument");
+    if (p->local) return fail(NW_ERR_UNSUPPORTED, "a local-alignment plan reports its best cell (nw_plan_best), not boundaries");
     if (p->mode == NW_MODE_SCORE) return fail(NW_ERR_STATE, "a score-mode plan only has a score");
     if (p->epoch == 0) return fail(NW_ERR_STATE, "no fill has been run");
     CK(cudaSetDevice(p->device));
@@ -1351,6 +1446,7 @@ extern "C" int nw_plan_traceback(nw_plan* p, int8_t* a1, int8_t* a2, int32_t* le
 {
     if (!p || !a1 || !a2 || !len) return fail(NW_ERR_ARG, "bad argument");
     if (p->mode != NW_MODE_FULL) return fail(NW_ERR_STATE, "traceback needs a full-table plan");
+    if (p->local) return fail(NW_ERR_UNSUPPORTED, "traceback of a local alignment is not implemented");
     if (p->nparts != 1 || p->streamed) return fail(NW_ERR_UNSUPPORTED, "traceback needs the whole table on one device");
     if (p->epoch == 0) return fail(NW_ERR_STATE, "no fill has been run");
     CK(cudaSetDevice(p->device));
@@ -1417,7 +1513,7 @@ extern "C" int nw_plan_strip_row(nw_plan* p, int strip, int32_t* row)
     CK(cudaSetDevice(p->device));
     const int row_i = p->n2 - (p->nstrips - 1 - strip) * 32 * p->R;
     nw::nw_strip_row_kernel<<<64, 256, 0, p->stream>>>(p->brow() + (long long)strip * p->pitch, p->ncols, row_i, p->jstart,
-                                                        p->d_tmp_row, p->sc_gap);
+                                                        p->d_tmp_row, p->local ? 0 : p->sc_gap);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(row, p->d_tmp_row, sizeof(int32_t) * ((size_t)p->ncols + 1), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
@@ -1441,6 +1537,9 @@ static std::vector<const void*> all_kernels()
     for (int R : {1, 2, 4, 8})
         for (int g = 0; g < 2; ++g)
             for (int f = 0; f < 2; ++f) v.push_back((const void*)strip_kernel(R, g != 0, f != 0));
+    for (int R : {1, 2, 4, 8})
+        for (int f = 0; f < 2; ++f) v.push_back((const void*)local_kernel(R, f != 0));
+    v.push_back((const void*)nw::nw_local_finish_kernel);
     for (int R : {4, 8, 16, 32})
         for (int g = 0; g < 2; ++g) v.push_back((const void*)batch_kernel(R, g != 0));
     for (int regs : {2, 4, 8, 16}) v.push_back((const void*)batch16_kernel(regs));
@@ -1555,7 +1654,8 @@ struct Trace {      // NW_CUDA_TRACE=1: wall-clock phases of a one-shot call on 
 }  // namespace
 
 static int run_pipeline(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int mode, int ngpus,
-                        int32_t* table, int32_t* last_row, int32_t* last_col, int32_t* score)
+                        int32_t* table, int32_t* last_row, int32_t* last_col, int32_t* score, const Scoring& sc = Scoring(),
+                        int32_t* end_i = nullptr, int32_t* end_j = nullptr)
 {
     Trace tr;
     if (ngpus < 1) return fail(NW_ERR_ARG, "ngpus must be >= 1");
@@ -1569,16 +1669,18 @@ static int run_pipeline(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t 
     static std::mutex cache_mu;
     static std::vector<nw_plan*> cache;
     static int c_n1 = -1, c_n2 = -1, c_mode = -1, c_ngpus = -1;
+    static Scoring c_sc;
     std::lock_guard<std::mutex> cache_lock(cache_mu);
     int rc = NW_OK;
-    if (!(c_n1 == n1 && c_n2 == n2 && c_mode == mode && c_ngpus == ngpus && (int)cache.size() == ngpus)) {
+    if (sc.local && ngpus != 1) return fail(NW_ERR_UNSUPPORTED, "local alignment is a single-device mode");
+    if (!(c_n1 == n1 && c_n2 == n2 && c_mode == mode && c_ngpus == ngpus && c_sc == sc && (int)cache.size() == ngpus)) {
         for (nw_plan* p : cache) nw_plan_destroy(p);
         cache.assign((size_t)ngpus, nullptr);
         nw_tuning tune;
         memset(&tune, 0, sizeof tune);
         for (int g = 0; g < ngpus && rc == NW_OK; ++g) {
             rc = plan_create_internal(&cache[g], g, n1, n2, mode, g, ngpus, g == 0 ? nullptr : &tune,
-                                      /*want_streamed=*/ngpus == 1 && mode == NW_MODE_FULL && table != nullptr);
+                                      /*want_streamed=*/ngpus == 1 && mode == NW_MODE_FULL && table != nullptr, sc);
             if (rc == NW_OK && g == 0) tune.rows_per_lane = cache[0]->R;     // all parts share the strip height
         }
         for (int g = 0; g + 1 < ngpus && rc == NW_OK; ++g) rc = nw_plan_connect(cache[g], cache[g + 1]);
@@ -1591,7 +1693,7 @@ static int run_pipeline(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t 
             c_n1 = -1;
             return rc;
         }
-        c_n1 = n1; c_n2 = n2; c_mode = mode; c_ngpus = ngpus;
+        c_n1 = n1; c_n2 = n2; c_mode = mode; c_ngpus = ngpus; c_sc = sc;
     }
     std::vector<nw_plan*>& plans = cache;
     tr.mark("plan_create");
@@ -1620,7 +1722,7 @@ static int run_pipeline(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t 
         }
     }
     tr.mark("table_to_host");
-    if (rc == NW_OK && score) rc = nw_plan_score(last, score);
+    if (rc == NW_OK && (score || end_i || end_j)) rc = nw_plan_best(last, score, end_i, end_j);
     if (rc == NW_OK && last_col) rc = nw_plan_last_col(last, last_col);
     if (rc == NW_OK && last_row)
         for (int g = 0; g < ngpus && rc == NW_OK; ++g) {
@@ -1645,22 +1747,25 @@ static int run_pipeline(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t 
 }
 
 // score only, through a cached NW_MODE_SCORE plan (what the reference driver reads in boundary mode: driver.cpp:35)
-static int run_score_oneshot(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int32_t* score)
+static int run_score_oneshot(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int32_t* score,
+                             const Scoring& sc = Scoring())
 {
     Trace tr;
     static std::mutex mu;
     static nw_plan* cached = nullptr;
     static int c_n1 = -1, c_n2 = -1;         // the caller's sizes (a score plan may hold them swapped)
+    static Scoring c_sc;
     std::lock_guard<std::mutex> lk(mu);
     int rc = NW_OK;
-    if (!cached || c_n1 != n1 || c_n2 != n2) {
+    if (!cached || c_n1 != n1 || c_n2 != n2 || !(c_sc == sc)) {
         if (cached) nw_plan_destroy(cached);
         cached = nullptr;
         c_n1 = c_n2 = -1;
-        rc = nw_plan_create(&cached, 0, n1, n2, NW_MODE_SCORE, 0, 1, nullptr);
+        rc = plan_create_internal(&cached, 0, n1, n2, NW_MODE_SCORE, 0, 1, nullptr, false, sc);
         if (rc) return rc;
         c_n1 = n1;
         c_n2 = n2;
+        c_sc = sc;
     }
     tr.mark("plan_create");
     rc = nw_plan_upload(cached, s1, s2);
@@ -1679,18 +1784,63 @@ static int run_score_oneshot(const int8_t* s1, int32_t n1, const int8_t* s2, int
     return rc;
 }
 
+static int fill_scored(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int32_t* table, int mode, int ngpus,
+                       const Scoring& sc)
+{
+    if (mode == NW_MODE_FULL) return run_pipeline(s1, n1, s2, n2, mode, ngpus, table, nullptr, nullptr, nullptr, sc);
+    if (mode != NW_MODE_BOUNDARY) return fail(NW_ERR_ARG, "unknown mode %d", mode);
+    int32_t score = 0;
+    int rc = (ngpus == 1 && !sc.local && !env_int("NW_CUDA_NO_BIDIR", 0))
+                 ? run_score_oneshot(s1, n1, s2, n2, &score, sc)
+                 : run_pipeline(s1, n1, s2, n2, mode, ngpus, nullptr, nullptr, nullptr, &score, sc);
+    if (rc == NW_OK) table[((long long)n1 + 1) * ((long long)n2 + 1) - 1] = score;     // what driver.cpp:35 reads
+    return rc;
+}
+
 extern "C" int nw_cuda_fill_ex(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int32_t* table, int mode,
                                int ngpus)
 {
     if (!table) return fail(NW_ERR_ARG, "table is NULL");
     if (n1 < 0 || n2 < 0) return fail(NW_ERR_ARG, "negative sequence length");
-    if (mode == NW_MODE_FULL) return run_pipeline(s1, n1, s2, n2, mode, ngpus, table, nullptr, nullptr, nullptr);
-    if (mode != NW_MODE_BOUNDARY) return fail(NW_ERR_ARG, "unknown mode %d", mode);
-    int32_t score = 0;
-    int rc = (ngpus == 1 && !env_int("NW_CUDA_NO_BIDIR", 0)) ? run_score_oneshot(s1, n1, s2, n2, &score)
-                                                            : run_pipeline(s1, n1, s2, n2, mode, ngpus, nullptr, nullptr, nullptr, &score);
-    if (rc == NW_OK) table[((long long)n1 + 1) * ((long long)n2 + 1) - 1] = score;     // what driver.cpp:35 reads
-    return rc;
+    return fill_scored(s1, n1, s2, n2, table, mode, ngpus, Scoring());
+}
+
+// mode < 0 / ngpus < 1: taken from NW_CUDA_MODE / NW_CUDA_GPUS like nw_cuda_fill (the reference driver's argv is fixed)
+extern "C" int nw_cuda_fill_scored(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int32_t* table, int mode,
+                                   int ngpus, const nw_scoring* scoring)
+{
+    if (!table) return fail(NW_ERR_ARG, "table is NULL");
+    if (n1 < 0 || n2 < 0) return fail(NW_ERR_ARG, "negative sequence length");
+    Scoring sc;
+    int rc = parse_scoring(scoring, n1, n2, &sc);
+    if (rc) return rc;
+    if (mode < 0) {
+        mode = NW_MODE_FULL;
+        const char* m = getenv("NW_CUDA_MODE");
+        if (m && *m) {
+            if (!strcmp(m, "boundary")) mode = NW_MODE_BOUNDARY;
+            else if (strcmp(m, "full")) return fail(NW_ERR_ARG, "NW_CUDA_MODE must be 'full' or 'boundary' (got '%s')", m);
+        }
+    }
+    if (ngpus < 1) ngpus = env_int("NW_CUDA_GPUS", 1);
+    return fill_scored(s1, n1, s2, n2, table, mode, ngpus, sc);
+}
+
+extern "C" int nw_cuda_score_scored(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, const nw_scoring* scoring,
+                                    int32_t* score, int32_t* end_i, int32_t* end_j)
+{
+    if (!score) return fail(NW_ERR_ARG, "score is NULL");
+    if (n1 < 0 || n2 < 0) return fail(NW_ERR_ARG, "negative sequence length");
+    Scoring sc;
+    int rc = parse_scoring(scoring, n1, n2, &sc);
+    if (rc) return rc;
+    if (!sc.local && !env_int("NW_CUDA_NO_BIDIR", 0)) {
+        rc = run_score_oneshot(s1, n1, s2, n2, score, sc);
+        if (rc == NW_OK && end_i) *end_i = n2;
+        if (rc == NW_OK && end_j) *end_j = n1;
+        return rc;
+    }
+    return run_pipeline(s1, n1, s2, n2, NW_MODE_BOUNDARY, 1, nullptr, nullptr, nullptr, score, sc, end_i, end_j);
 }
 
 extern "C" int nw_cuda_fill(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int32_t* table)
@@ -1861,6 +2011,18 @@ static int batch_scan(nw_batch* b)
     return NW_OK;
 }
 
+extern "C" int nw_batch_set_scoring(nw_batch* b, const nw_scoring* scoring)
+{
+    if (!b) return fail(NW_ERR_ARG, "batch is NULL");
+    Scoring sc;
+    int rc = parse_scoring(scoring, b->len1, b->len2, &sc);
+    if (rc) return rc;
+    if (sc.local) return fail(NW_ERR_UNSUPPORTED, "batches are global alignments");
+    b->sc_match = sc.match; b->sc_mis = sc.mismatch; b->sc_gap = sc.gap;
+    b->uploaded = false;       // the kernel choice depends on the weights: upload again
+    return NW_OK;
+}
+
 extern "C" int nw_batch_upload(nw_batch* b, const int8_t* S1, const int8_t* S2)
 {
     if (!b) return fail(NW_ERR_ARG, "batch is NULL");
@@ -1962,8 +2124,15 @@ extern "C" int nw_batch_scores(nw_batch* b, int32_t* scores)
 extern "C" int nw_cuda_batch_scores(const int8_t* S1, const int8_t* S2, int64_t npairs, int32_t len1, int32_t len2,
                                     int32_t* scores, int device)
 {
+    return nw_cuda_batch_scores_scored(S1, S2, npairs, len1, len2, nullptr, scores, device);
+}
+
+extern "C" int nw_cuda_batch_scores_scored(const int8_t* S1, const int8_t* S2, int64_t npairs, int32_t len1, int32_t len2,
+                                           const nw_scoring* scoring, int32_t* scores, int device)
+{
     nw_batch* b = nullptr;
     int rc = nw_batch_create(&b, device, npairs, len1, len2);
+    if (rc == NW_OK && scoring) rc = nw_batch_set_scoring(b, scoring);
     if (rc == NW_OK) rc = nw_batch_upload(b, S1, S2);
     if (rc == NW_OK) rc = nw_batch_run(b);
     if (rc == NW_OK) rc = nw_batch_scores(b, scores);

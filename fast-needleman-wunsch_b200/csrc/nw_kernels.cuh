@@ -104,6 +104,7 @@ struct StripParams {
     unsigned long long spin_ns;  // not hang us.  Waiting warps re-read only the DEVICE word (a host read costs microseconds).
     int w_match, w_mis;          // G-form weights: max(M - 2g, 0), max(X - 2g, 0)  (default scoring: 3, 2)
     int gap;                     // g (default -1): H = G + g*(i + j) where cells leave a kernel
+    int4* local_best;            // local alignment (nw_local.cuh): per strip {best score, row, column, 0}
     int margin;                  // packed kernels: slack below the warp's minimum when re-basing (2 * max weight + 10)
     unsigned long long* times;   // nstrips x 4: %globaltimer (ns) when a strip has its first top-row block and when it
                                  // ends, then clock64 (SM cycles) at the same two points -- the trace behind the start-up

@@ -25,6 +25,8 @@ EXPORTS = [
     "nw_plan_table_to_host", "nw_plan_table_device", "nw_plan_traceback", "nw_plan_strip_info", "nw_plan_strip_row", "nw_plan_strip_times",
     "nw_batch_create", "nw_batch_destroy", "nw_batch_upload", "nw_batch_upload_device", "nw_batch_run",
     "nw_batch_sync", "nw_batch_time", "nw_batch_scores", "nw_cuda_dpx_peak",
+    "nw_cuda_fill_scored", "nw_cuda_score_scored", "nw_cuda_batch_scores_scored", "nw_plan_create_scored", "nw_plan_best",
+    "nw_batch_set_scoring",
 ]
 
 
@@ -34,6 +36,22 @@ class NwCudaError(RuntimeError):
 
 class Tuning(C.Structure):
     _fields_ = [("rows_per_lane", C.c_int), ("warps_per_cta", C.c_int), ("ctas", C.c_int), ("reserved", C.c_int * 5)]
+
+
+class Scoring(C.Structure):
+    """nw_scoring: match / mismatch / gap (the reference's macros, src/common/needleman-wunsch.hpp:11-13, are 1, 0, -1);
+    local=1 selects Smith-Waterman."""
+    _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("gap", C.c_int32), ("local", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
+
+
+def _scoring(scoring):
+    """None | Scoring | (match, mismatch, gap[, local]) -> pointer argument"""
+    if scoring is None:
+        return None
+    if not isinstance(scoring, Scoring):
+        scoring = Scoring(*[int(x) for x in scoring])
+    return C.byref(scoring)
 
 
 _lib = None
@@ -74,6 +92,13 @@ def lib():
             "nw_batch_sync": [vp], "nw_batch_time": [vp, C.c_int, C.POINTER(C.c_float)],
             "nw_batch_scores": [vp, vp],
             "nw_cuda_dpx_peak": [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)],
+            "nw_cuda_fill_scored": [vp, i32, vp, i32, vp, C.c_int, C.c_int, C.POINTER(Scoring)],
+            "nw_cuda_score_scored": [vp, i32, vp, i32, C.POINTER(Scoring), vp, vp, vp],
+            "nw_cuda_batch_scores_scored": [vp, vp, i64, i32, i32, C.POINTER(Scoring), vp, C.c_int],
+            "nw_plan_create_scored": [C.POINTER(vp), C.c_int, i32, i32, C.c_int, C.c_int, C.c_int, C.POINTER(Tuning),
+                                      C.POINTER(Scoring)],
+            "nw_plan_best": [vp, vp, vp, vp],
+            "nw_batch_set_scoring": [vp, C.POINTER(Scoring)],
         }
         for name, args in sigs.items():
             f = getattr(L, name)
@@ -131,7 +156,7 @@ def device_info(device=0):
     return {"name": name.value.decode(), "sm_count": sms.value, "sm_clock_mhz": mhz.value}
 
 
-def needlemanWunsch(s1, s2, t=None, mode=NW_MODE_FULL, ngpus=1):
+def needlemanWunsch(s1, s2, t=None, mode=NW_MODE_FULL, ngpus=1, scoring=None):
     """Fill the table like the reference's needlemanWunsch(dnaArray s1, dnaArray s2, int* t)
     (src/serial/serial.cpp:4-36): s1 across (columns), s2 down (rows), t row-major int32 (n2+1) x (n1+1).
     In boundary mode only t[-1, -1] (the score, driver.cpp:35) is written.  Returns t."""
@@ -140,15 +165,30 @@ def needlemanWunsch(s1, s2, t=None, mode=NW_MODE_FULL, ngpus=1):
         t = np.empty((s2.size + 1, s1.size + 1), dtype=np.int32)
     if t.dtype != np.int32 or not t.flags.c_contiguous or t.size != (s1.size + 1) * (s2.size + 1):
         raise ValueError("t must be a C-contiguous int32 array of (n2+1)*(n1+1) elements")
-    _ck(lib().nw_cuda_fill_ex(_ptr(s1), s1.size, _ptr(s2), s2.size, t.ctypes.data, mode, ngpus))
+    if scoring is None:
+        _ck(lib().nw_cuda_fill_ex(_ptr(s1), s1.size, _ptr(s2), s2.size, t.ctypes.data, mode, ngpus))
+    else:
+        _ck(lib().nw_cuda_fill_scored(_ptr(s1), s1.size, _ptr(s2), s2.size, t.ctypes.data, mode, ngpus, _scoring(scoring)))
     return t
 
 
-def score(s1, s2):
+def score(s1, s2, scoring=None):
     s1, s2 = _seq(s1), _seq(s2)
     out = C.c_int32()
-    _ck(lib().nw_cuda_score(_ptr(s1), s1.size, _ptr(s2), s2.size, C.byref(out)))
+    if scoring is None:
+        _ck(lib().nw_cuda_score(_ptr(s1), s1.size, _ptr(s2), s2.size, C.byref(out)))
+    else:
+        _ck(lib().nw_cuda_score_scored(_ptr(s1), s1.size, _ptr(s2), s2.size, _scoring(scoring), C.byref(out), None, None))
     return out.value
+
+
+def best(s1, s2, scoring):
+    """(score, end_i, end_j): for local alignment (scoring.local = 1) the best cell of the Smith-Waterman table (smallest
+    column, then smallest row among equals; (0, 0) when the score is 0); for global alignment (H[n2][n1], n2, n1)."""
+    s1, s2 = _seq(s1), _seq(s2)
+    sc, i, j = C.c_int32(), C.c_int32(), C.c_int32()
+    _ck(lib().nw_cuda_score_scored(_ptr(s1), s1.size, _ptr(s2), s2.size, _scoring(scoring), C.byref(sc), C.byref(i), C.byref(j)))
+    return sc.value, i.value, j.value
 
 
 def boundaries(s1, s2):
@@ -161,13 +201,13 @@ def boundaries(s1, s2):
     return row, col, out.value
 
 
-def batch_scores(S1, S2, device=0):
+def batch_scores(S1, S2, device=0, scoring=None):
     S1, S2 = _seq(S1), _seq(S2)
     if S1.ndim != 2 or S2.ndim != 2 or S1.shape[0] != S2.shape[0]:
         raise ValueError("S1 is npairs x len1, S2 is npairs x len2")
     out = np.empty(S1.shape[0], dtype=np.int32)
-    _ck(lib().nw_cuda_batch_scores(_ptr(S1), _ptr(S2), S1.shape[0], S1.shape[1], S2.shape[1],
-                                   out.ctypes.data if out.size else None, device))
+    _ck(lib().nw_cuda_batch_scores_scored(_ptr(S1), _ptr(S2), S1.shape[0], S1.shape[1], S2.shape[1], _scoring(scoring),
+                                          out.ctypes.data if out.size else None, device))
     return out
 
 
@@ -190,11 +230,15 @@ class Plan:
     """Device-resident fill state (nw_plan_* of include/nw_cuda.h)."""
 
     def __init__(self, n1, n2, mode=NW_MODE_BOUNDARY, device=0, part=0, nparts=1, rows_per_lane=0, warps_per_cta=0,
-                 ctas=0):
+                 ctas=0, scoring=None):
         self.n1, self.n2, self.mode, self.device, self.part, self.nparts = n1, n2, mode, device, part, nparts
         self._h = C.c_void_p()
         tune = Tuning(rows_per_lane, warps_per_cta, ctas)
-        _ck(lib().nw_plan_create(C.byref(self._h), device, n1, n2, mode, part, nparts, C.byref(tune)))
+        if scoring is None:
+            _ck(lib().nw_plan_create(C.byref(self._h), device, n1, n2, mode, part, nparts, C.byref(tune)))
+        else:
+            _ck(lib().nw_plan_create_scored(C.byref(self._h), device, n1, n2, mode, part, nparts, C.byref(tune),
+                                            _scoring(scoring)))
         start, owned = strip_partition(n1, nparts, part)
         self.jstart, self.ncols = start, owned - 1
 
@@ -265,6 +309,11 @@ class Plan:
         _ck(lib().nw_plan_score(self._h, C.byref(out)))
         return out.value
 
+    def best(self):
+        sc, i, j = C.c_int32(), C.c_int32(), C.c_int32()
+        _ck(lib().nw_plan_best(self._h, C.byref(sc), C.byref(i), C.byref(j)))
+        return sc.value, i.value, j.value
+
     def last_row(self):
         out = np.empty(self.ncols + 1, dtype=np.int32)
         _ck(lib().nw_plan_last_row(self._h, out.ctypes.data))
@@ -315,10 +364,12 @@ class Plan:
 class Batch:
     """Batch of independent pairs on one device (nw_batch_* of include/nw_cuda.h)."""
 
-    def __init__(self, npairs, len1, len2, device=0):
+    def __init__(self, npairs, len1, len2, device=0, scoring=None):
         self.npairs, self.len1, self.len2, self.device = npairs, len1, len2, device
         self._h = C.c_void_p()
         _ck(lib().nw_batch_create(C.byref(self._h), device, npairs, len1, len2))
+        if scoring is not None:
+            _ck(lib().nw_batch_set_scoring(self._h, _scoring(scoring)))
 
     def close(self):
         if self._h:

@@ -81,6 +81,35 @@ int nw_cuda_batch_scores(const int8_t* S1, const int8_t* S2, int64_t npairs, int
                          int32_t* scores, int device);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Scoring parameters and local alignment.
+ *
+ * The reference's only scoring configuration is the three compile-time macros MATCH / MISMATCH / GAP of
+ * src/common/needleman-wunsch.hpp:11-13 (1, 0, -1); its README.md:2 names Smith-Waterman as a goal.  A NULL
+ * nw_scoring* means exactly those macros.  Any integers are accepted as long as every table value fits int32
+ * (checked at plan creation); local alignment additionally needs gap <= 0.
+ *   local = 0: global alignment (Needleman-Wunsch), H[0][j] = gap*j, H[i][0] = gap*i, bit-exact against serial.cpp built
+ *              with the same three macros.
+ *   local = 1: Smith-Waterman, H = max(0, diag + s, up + gap, left + gap) with a zero first row and column; the
+ *              result is the best cell and its position (smallest column first, then smallest row; (0,0) if the
+ *              best score is 0).  Single device; NW_MODE_BOUNDARY (score + end position + checkpoint rows) or
+ *              NW_MODE_FULL (the whole H table as well).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct nw_scoring {
+    int32_t match, mismatch, gap;
+    int32_t local;
+    int32_t reserved[4];     /* must be 0 */
+} nw_scoring;
+
+/* nw_cuda_fill_ex / nw_cuda_score with explicit scoring (what csrc/cuda.cpp passes from the reference's macros).
+ * end_i / end_j (may be NULL): position of the reported cell -- (n2, n1) for global alignment. */
+int nw_cuda_fill_scored(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int32_t* table,
+                        int mode, int ngpus, const nw_scoring* scoring);
+int nw_cuda_score_scored(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, const nw_scoring* scoring,
+                         int32_t* score, int32_t* end_i, int32_t* end_j);
+int nw_cuda_batch_scores_scored(const int8_t* S1, const int8_t* S2, int64_t npairs, int32_t len1, int32_t len2,
+                                const nw_scoring* scoring /* global only */, int32_t* scores, int device);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Plans: device-resident state for repeated / timed / multi-GPU runs.
  *
  * A plan owns, on one device, the encoded sequences, the strip boundary rows, the progress flags and (in full
@@ -104,6 +133,9 @@ typedef struct nw_tuning {
  * sequences (always true for bdna), 32-bit kernels otherwise. */
 int nw_plan_create(nw_plan** out, int device, int32_t n1, int32_t n2, int mode,
                    int part, int nparts, const nw_tuning* tuning /* may be NULL */);
+/* The same with scoring parameters (NULL = the reference's macros). */
+int nw_plan_create_scored(nw_plan** out, int device, int32_t n1, int32_t n2, int mode,
+                          int part, int nparts, const nw_tuning* tuning, const nw_scoring* scoring);
 int nw_plan_destroy(nw_plan* p);
 
 /* Sequences from HOST memory (H2D inside).  Every part receives the FULL s1 and s2, like every MPI rank loads
@@ -137,6 +169,8 @@ int nw_plan_launches_per_run(nw_plan* p, int* n);
 
 /* Results (D2H inside; synchronises the plan's stream).  Valid on the LAST part of a pipeline. */
 int nw_plan_score(nw_plan* p, int32_t* score);
+/* Reported cell: global alignment (n2, n1) and H[n2][n1]; local alignment the best cell (see nw_scoring). */
+int nw_plan_best(nw_plan* p, int32_t* score, int32_t* end_i, int32_t* end_j);
 int nw_plan_last_row(nw_plan* p, int32_t* last_row /* ncols of this part, H values */);
 int nw_plan_last_col(nw_plan* p, int32_t* last_col /* n2+1 H values of this part's right-most column */);
 /* Full mode only: copy this part's columns into a HOST table with row pitch (n1+1). */
@@ -164,6 +198,7 @@ int nw_plan_strip_times(nw_plan* p, int64_t* start_ns, int64_t* end_ns, int64_t*
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct nw_batch nw_batch;
 int nw_batch_create(nw_batch** out, int device, int64_t npairs, int32_t len1, int32_t len2);
+int nw_batch_set_scoring(nw_batch* b, const nw_scoring* scoring);   /* before nw_batch_upload; global alignment only */
 int nw_batch_destroy(nw_batch* b);
 int nw_batch_upload(nw_batch* b, const int8_t* S1, const int8_t* S2);            /* HOST -> device */
 int nw_batch_upload_device(nw_batch* b, const int8_t* d_S1, const int8_t* d_S2);

@@ -12,6 +12,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 BDNA = os.path.join(ROOT, "oracle", "_ref", "bdna")
 GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))
+GOLDEN_SCORING = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_scoring.json")))
 
 
 def pytest_configure(config):
@@ -63,6 +64,12 @@ class Oracle:
         L.nw_oracle_strip.restype = i32
         L.nw_oracle_traceback.argtypes = [vp, i32, vp, i32, vp, vp]
         L.nw_oracle_traceback.restype = i32
+        L.nw_oracle_fill_ex.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, vp]
+        L.nw_oracle_fill_ex.restype = None
+        L.nw_oracle_score_ex.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+        L.nw_oracle_score_ex.restype = i32
+        L.nw_oracle_traceback_ex.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp]
+        L.nw_oracle_traceback_ex.restype = i32
         L.nw_oracle_fnv1a64.argtypes = [vp, i64]
         L.nw_oracle_fnv1a64.restype = C.c_uint64
         L.nw_oracle_fnv1a64_col.argtypes = [vp, i64, i64]
@@ -111,6 +118,27 @@ class Oracle:
         a1 = np.empty(s1.size + s2.size + 1, dtype=np.int8)
         a2 = np.empty(s1.size + s2.size + 1, dtype=np.int8)
         n = self.L.nw_oracle_traceback(self._p(s1), s1.size, self._p(s2), s2.size, a1.ctypes.data, a2.ctypes.data)
+        return a1[:n].copy(), a2[:n].copy()
+
+    def fill_ex(self, s1, s2, scoring):
+        """scoring = (match, mismatch, gap[, local])"""
+        m, x, g, local = (list(scoring) + [0])[:4]
+        t = np.empty((s2.size + 1, s1.size + 1), dtype=np.int32)
+        self.L.nw_oracle_fill_ex(self._p(s1), s1.size, self._p(s2), s2.size, m, x, g, local, t.ctypes.data)
+        return t
+
+    def score_ex(self, s1, s2, scoring):
+        """(score, end_i, end_j)"""
+        m, x, g, local = (list(scoring) + [0])[:4]
+        i, j = C.c_int32(), C.c_int32()
+        sc = self.L.nw_oracle_score_ex(self._p(s1), s1.size, self._p(s2), s2.size, m, x, g, local, C.byref(i), C.byref(j))
+        return int(sc), i.value, j.value
+
+    def traceback_ex(self, s1, s2, scoring):
+        m, x, g = scoring[:3]
+        a1 = np.empty(s1.size + s2.size + 1, dtype=np.int8)
+        a2 = np.empty(s1.size + s2.size + 1, dtype=np.int8)
+        n = self.L.nw_oracle_traceback_ex(self._p(s1), s1.size, self._p(s2), s2.size, m, x, g, a1.ctypes.data, a2.ctypes.data)
         return a1[:n].copy(), a2[:n].copy()
 
     def fnv(self, a):
