@@ -6,7 +6,7 @@ the tests and bench.py.  Import it with importlib (the directory name has a hyph
     nw = importlib.import_module("fast-needleman-wunsch_b200")
 """
 from .nwcuda import (  # noqa: F401
-    NW_MODE_BOUNDARY, NW_MODE_FULL, NW_MODE_SCORE, NwCudaError, Plan, Batch, Scoring, best, lib, lib_path,
+    NW_MODE_BOUNDARY, NW_MODE_FULL, NW_MODE_SCORE, NwCudaError, Plan, Batch, Scoring, best, align, plans_traceback, lib, lib_path,
     readSequence, printSequence, needlemanWunsch, score, boundaries, batch_scores, dpx_peak, device_count, device_info, init,
     strip_partition,
 )

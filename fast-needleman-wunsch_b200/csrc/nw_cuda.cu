@@ -291,6 +291,7 @@ struct nw_plan {
     int4* d_local_best = nullptr;              // local alignment: best cell per strip
     size_t local_best_n = 0;
 
+    bool mailbox_pooled = false;     // the mailbox comes from the device's pool (same-device pipelines: no IPC, no peers)
     int2* d_mailbox = nullptr;       // 2 x mpitch tagged words: halo of parts > 0 (double-buffered by epoch parity)
     int2* d_rcol_local = nullptr;    // 2 x mpitch: right column when nobody is connected on the right
     long long mpitch = 0;
@@ -459,8 +460,9 @@ extern "C" int nw_plan_destroy(nw_plan* p)
                     p->d_local_best};
     for (void* b : bufs)
         if (b) cudaFreeAsync(b, p->stream ? p->stream : (cudaStream_t)0);      // back into the device's pool
+    if (p->d_mailbox && p->mailbox_pooled) cudaFreeAsync(p->d_mailbox, p->stream ? p->stream : (cudaStream_t)0);
     if (p->stream) cudaStreamSynchronize(p->stream);
-    if (p->d_mailbox) cudaFree(p->d_mailbox);
+    if (p->d_mailbox && !p->mailbox_pooled) cudaFree(p->d_mailbox);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->ev2) cudaEventDestroy(p->ev2);
@@ -502,7 +504,8 @@ static int plan_alloc(nw_plan* p, const nw_tuning* tuning)
     p->mpitch = ((long long)n2 + 1 + 15) & ~15LL;
     if (p->part > 0) {
         // cudaMalloc, not the pool: the mailbox is exported to other processes as a CUDA IPC handle and written by peers
-        CK(cudaMalloc(&p->d_mailbox, sizeof(int2) * 2 * (size_t)p->mpitch + 64));
+        if (p->mailbox_pooled) CK(dev_alloc(p->device, p->stream, &p->d_mailbox, sizeof(int2) * 2 * (size_t)p->mpitch + 64));
+        else CK(cudaMalloc(&p->d_mailbox, sizeof(int2) * 2 * (size_t)p->mpitch + 64));
         CK(cudaMemsetAsync(p->d_mailbox, 0, sizeof(int2) * 2 * (size_t)p->mpitch + 64, p->stream));
     }
     CK(dev_alloc(p->device, p->stream, &p->d_rcol_local, sizeof(int2) * 2 * (size_t)p->mpitch));
@@ -658,7 +661,7 @@ static int plan_pick_kernel(nw_plan* p)
 }
 
 static int plan_create_internal(nw_plan** out, int device, int32_t n1, int32_t n2, int mode, int part, int nparts,
-                                const nw_tuning* tuning, bool want_streamed, const Scoring& sc);
+                                const nw_tuning* tuning, bool want_streamed, const Scoring& sc, bool same_device_pipeline = false);
 
 extern "C" int nw_plan_create(nw_plan** out, int device, int32_t n1, int32_t n2, int mode, int part, int nparts,
                               const nw_tuning* tuning)
@@ -678,7 +681,7 @@ extern "C" int nw_plan_create_scored(nw_plan** out, int device, int32_t n1, int3
 }
 
 static int plan_create_internal(nw_plan** out, int device, int32_t n1, int32_t n2, int mode, int part, int nparts,
-                                const nw_tuning* tuning, bool want_streamed, const Scoring& sc)
+                                const nw_tuning* tuning, bool want_streamed, const Scoring& sc, bool same_device_pipeline)
 {
     if (!out) return fail(NW_ERR_ARG, "out is NULL");
     *out = nullptr;
@@ -733,6 +736,7 @@ static int plan_create_internal(nw_plan** out, int device, int32_t n1, int32_t n
     p->nparts = nparts;
     p->sc_match = sc.match; p->sc_mis = sc.mismatch; p->sc_gap = sc.gap; p->local = sc.local != 0;
     p->want_streamed = want_streamed;
+    p->mailbox_pooled = same_device_pipeline;
     partition(n1, nparts, part, &p->jstart, &p->ncols);
     rc = plan_alloc(p, tuning);
     if (rc == NW_OK) rc = plan_pick_kernel(p);        // provisional (assumes the four-letter alphabet) so that
@@ -868,6 +872,7 @@ extern "C" int nw_plan_connect(nw_plan* left, nw_plan* right)
 extern "C" int nw_plan_export_mailbox(nw_plan* p, void* handle64)
 {
     if (!p || !handle64) return fail(NW_ERR_ARG, "NULL argument");
+    if (p->mailbox_pooled) return fail(NW_ERR_STATE, "this plan's mailbox is pool memory (same-device pipeline)");
     if (p->mode == NW_MODE_SCORE) return fail(NW_ERR_UNSUPPORTED, "score mode is a single-device mode");
     if (p->part == 0) return fail(NW_ERR_STATE, "part 0 has no halo mailbox");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -1442,37 +1447,202 @@ extern "C" int nw_plan_table_device(nw_plan* p, int32_t** d_table, int64_t* pitc
     return NW_OK;
 }
 
-extern "C" int nw_plan_traceback(nw_plan* p, int8_t* a1, int8_t* a2, int32_t* len)
+#include <chrono>
+namespace {
+struct Trace {      // NW_CUDA_TRACE=1: wall-clock phases of a one-shot call on stderr (stdout belongs to the driver)
+    bool on = env_int("NW_CUDA_TRACE", 0) != 0;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char* what)
+    {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[nw_cuda] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+}  // namespace
+
+// the kernels emit the path backwards into d_out[0..cap) / d_out[cap..2cap); *d_n = its length
+static int fetch_reversed_path(cudaStream_t st, const uint8_t* d_out, size_t cap, const int* d_n, int8_t* a1, int8_t* a2, int32_t* len)
 {
-    if (!p || !a1 || !a2 || !len) return fail(NW_ERR_ARG, "bad argument");
-    if (p->mode != NW_MODE_FULL) return fail(NW_ERR_STATE, "traceback needs a full-table plan");
-    if (p->local) return fail(NW_ERR_UNSUPPORTED, "traceback of a local alignment is not implemented");
-    if (p->nparts != 1 || p->streamed) return fail(NW_ERR_UNSUPPORTED, "traceback needs the whole table on one device");
-    if (p->epoch == 0) return fail(NW_ERR_STATE, "no fill has been run");
-    CK(cudaSetDevice(p->device));
-    const size_t cap = (size_t)p->n1 + (size_t)p->n2 + 1;
-    uint8_t* d_out = nullptr;
-    int* d_len = nullptr;
-    CK(cudaMalloc(&d_out, 2 * cap));
-    CK(cudaMalloc(&d_len, sizeof(int)));
-    nw::nw_traceback_kernel<<<1, 256, 0, p->stream>>>(p->d_table, p->tpitch, p->d_s1, p->d_s2, p->n1, p->n2, d_out,
-                                                      d_out + cap, d_len, p->sc_match, p->sc_mis, p->sc_gap);
-    cudaError_t e = cudaGetLastError();
     int n = 0;
     std::vector<uint8_t> r1(cap), r2(cap);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&n, d_len, sizeof(int), cudaMemcpyDeviceToHost, p->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(r1.data(), d_out, cap, cudaMemcpyDeviceToHost, p->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(r2.data(), d_out + cap, cap, cudaMemcpyDeviceToHost, p->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
-    cudaFree(d_out);
-    cudaFree(d_len);
-    if (e != cudaSuccess) return fail(NW_ERR_CUDA, "traceback: %s", cudaGetErrorString(e));
-    for (int k = 0; k < n; ++k) {            // the kernel emits the path backwards
+    CK(cudaMemcpyAsync(&n, d_n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(r1.data(), d_out, cap, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(r2.data(), d_out + cap, cap, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n < 0 || (size_t)n > cap) return fail(NW_ERR_CUDA, "traceback: bad path length %d", n);
+    for (int k = 0; k < n; ++k) {
         a1[k] = (int8_t)r1[(size_t)n - 1 - k];
         a2[k] = (int8_t)r2[(size_t)n - 1 - k];
     }
     *len = n;
     return NW_OK;
+}
+
+// Traceback from the checkpoint rows and columns of boundary-mode parts (nw_tile_trace_kernel): no table anywhere.
+extern "C" int nw_plans_traceback(nw_plan* const* parts, int nparts, int8_t* a1, int8_t* a2, int32_t* len)
+{
+    if (!parts || nparts < 1 || !a1 || !a2 || !len) return fail(NW_ERR_ARG, "bad argument");
+    nw_plan* p0 = parts[0];
+    for (int g = 0; g < nparts; ++g) {
+        nw_plan* q = parts[g];
+        if (!q) return fail(NW_ERR_ARG, "part %d is NULL", g);
+        if (q->mode != NW_MODE_BOUNDARY || q->local) return fail(NW_ERR_STATE, "checkpoint traceback needs boundary-mode global-alignment plans");
+        if (q->nparts != nparts || q->part != g || q->n1 != p0->n1 || q->n2 != p0->n2 || q->device != p0->device)
+            return fail(NW_ERR_ARG, "plans are not the %d parts of one pipeline on one device", nparts);
+        if (q->epoch == 0 || q->epoch != p0->epoch) return fail(NW_ERR_STATE, "the parts have not all run the same fill");
+        if (q->R != p0->R || q->nstrips != p0->nstrips || q->pad_top != p0->pad_top) return fail(NW_ERR_STATE, "the parts differ in strip height");
+        if (q->sc_match != p0->sc_match || q->sc_mis != p0->sc_mis || q->sc_gap != p0->sc_gap) return fail(NW_ERR_ARG, "the parts differ in scoring");
+        if (g > 0 && parts[g - 1]->rcol_target != q->d_mailbox) return fail(NW_ERR_STATE, "part %d is not connected to part %d", g - 1, g);
+    }
+    const int SH = 32 * p0->R;
+    if (SH > nw::TT_MAX_ROWS) return fail(NW_ERR_UNSUPPORTED, "strip height %d exceeds %d", SH, nw::TT_MAX_ROWS);
+    CK(cudaSetDevice(p0->device));
+    for (int g = 0; g < nparts; ++g) {
+        CK(cudaStreamSynchronize(parts[g]->stream));
+        int rc = check_abort(parts[g]->device);
+        if (rc) return rc;
+    }
+    nw_plan* last = parts[nparts - 1];
+    cudaStream_t st = last->stream;
+    const int dev = p0->device;
+    const size_t cap = (size_t)p0->n1 + (size_t)p0->n2 + 1;
+    int maxcols = 0;
+    for (int g = 0; g < nparts; ++g) maxcols = std::max(maxcols, parts[g]->ncols);
+    const long long spitch = ((long long)std::max(maxcols, SH) + 1 + 7) & ~7LL;
+    // phase-major cells: (blocks of the widest part + rows) phases x TT_B x SH
+    const size_t scratch_ints = 2 * (size_t)spitch + ((size_t)(maxcols + nw::TT_B - 1) / nw::TT_B + (size_t)SH) * nw::TT_B * (size_t)SH;
+    uint8_t *d_out = nullptr, *d_s1 = nullptr;
+    int32_t* d_scratch = nullptr;
+    int* d_state = nullptr;
+    nw::TracePart* d_parts = nullptr;
+    std::vector<nw::TracePart> hp((size_t)nparts);
+    for (int g = 0; g < nparts; ++g) {
+        nw_plan* q = parts[g];
+        hp[g].brow = q->brow();
+        hp[g].pitch = q->pitch;
+        hp[g].halo = (g > 0) ? q->d_mailbox + (long long)(q->epoch & 1) * q->mpitch : nullptr;
+        hp[g].jstart = q->jstart;
+        hp[g].ncols = q->ncols;
+    }
+    int rc = NW_OK;
+    auto body = [&]() -> int {
+        CK(dev_alloc(dev, st, &d_out, 2 * cap));
+        CK(dev_alloc(dev, st, &d_s1, (size_t)std::max(p0->n1, 1)));
+        CK(dev_alloc(dev, st, &d_scratch, sizeof(int32_t) * scratch_ints));
+        CK(dev_alloc(dev, st, &d_state, 8 * sizeof(int)));
+        CK(dev_alloc(dev, st, &d_parts, sizeof(nw::TracePart) * (size_t)nparts));
+        for (int g = 0; g < nparts; ++g)       // the whole s1 back together from the parts' slices
+            if (parts[g]->ncols > 0)
+                CK(cudaMemcpyAsync(d_s1 + parts[g]->jstart, parts[g]->d_s1, (size_t)parts[g]->ncols, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(d_parts, hp.data(), sizeof(nw::TracePart) * (size_t)nparts, cudaMemcpyHostToDevice, st));
+        const int state0[8] = {p0->n2, p0->n1, 0, 0, 0, 0, 0, 0};
+        CK(cudaMemcpyAsync(d_state, state0, sizeof state0, cudaMemcpyHostToDevice, st));
+        nw::TraceParams tp;
+        tp.parts = d_parts;
+        tp.nparts = nparts;
+        tp.s1 = d_s1;
+        tp.s2 = last->d_s2;
+        tp.n1 = p0->n1; tp.n2 = p0->n2; tp.nstrips = p0->nstrips; tp.strip_rows = SH; tp.pad_top = p0->pad_top;
+        tp.sc_match = p0->sc_match; tp.sc_mis = p0->sc_mis; tp.sc_gap = p0->sc_gap;
+        tp.scratch = d_scratch;
+        tp.spitch = spitch;
+        tp.rpitch = SH;
+        tp.state = d_state;
+        tp.out1 = d_out;
+        tp.out2 = d_out + cap;
+        // a monotone path visits at most one tile per strip plus one per part, then one launch for the forced tail
+        const int launches = std::max(p0->nstrips, 0) + nparts + 2;
+        for (int k = 0; k < launches; ++k) nw::nw_tile_trace_kernel<<<1, SH, 0, st>>>(tp);
+        CK(cudaGetLastError());
+        int state[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        CK(cudaMemcpyAsync(state, d_state, sizeof state, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (env_int("NW_CUDA_TRACE", 0))
+            fprintf(stderr, "[nw_cuda] tile traceback: %d tiles of %d launches, fill %.1f Mcycles in %d block steps, walk %.1f Mcycles\n",
+                    state[4], launches, state[5] * 1024e-6, state[7], state[6] * 1024e-6);
+        if (state[3] != 0 || state[0] != 0 || state[1] != 0)
+            return fail(NW_ERR_CUDA, "checkpoint traceback did not finish (stopped at %d, %d, flag %d)", state[0], state[1], state[3]);
+        return fetch_reversed_path(st, d_out, cap, d_state + 2, a1, a2, len);
+    };
+    rc = body();
+    void* bufs[] = {d_out, d_s1, d_scratch, d_state, d_parts};
+    for (void* b : bufs)
+        if (b) cudaFreeAsync(b, st);
+    cudaStreamSynchronize(st);
+    return rc;
+}
+
+extern "C" int nw_plan_traceback(nw_plan* p, int8_t* a1, int8_t* a2, int32_t* len)
+{
+    if (!p || !a1 || !a2 || !len) return fail(NW_ERR_ARG, "bad argument");
+    if (p->mode == NW_MODE_BOUNDARY) {          // from the checkpoint rows: no table
+        if (p->nparts != 1) return fail(NW_ERR_ARG, "a pipeline is traced back through nw_plans_traceback (all its parts)");
+        nw_plan* one[1] = {p};
+        return nw_plans_traceback(one, 1, a1, a2, len);
+    }
+    if (p->mode != NW_MODE_FULL) return fail(NW_ERR_STATE, "traceback needs a boundary-mode or full-table plan");
+    if (p->local) return fail(NW_ERR_UNSUPPORTED, "traceback of a local alignment is not implemented");
+    if (p->nparts != 1 || p->streamed) return fail(NW_ERR_UNSUPPORTED, "table traceback needs the whole table on one device");
+    if (p->epoch == 0) return fail(NW_ERR_STATE, "no fill has been run");
+    CK(cudaSetDevice(p->device));
+    const size_t cap = (size_t)p->n1 + (size_t)p->n2 + 1;
+    uint8_t* d_out = nullptr;
+    int* d_len = nullptr;
+    CK(dev_alloc(p->device, p->stream, &d_out, 2 * cap));
+    CK(dev_alloc(p->device, p->stream, &d_len, sizeof(int)));
+    nw::nw_traceback_kernel<<<1, 256, 0, p->stream>>>(p->d_table, p->tpitch, p->d_s1, p->d_s2, p->n1, p->n2, d_out,
+                                                      d_out + cap, d_len, p->sc_match, p->sc_mis, p->sc_gap);
+    int rc = (cudaGetLastError() == cudaSuccess) ? NW_OK : fail(NW_ERR_CUDA, "traceback launch failed");
+    if (rc == NW_OK) rc = fetch_reversed_path(p->stream, d_out, cap, d_len, a1, a2, len);
+    cudaFreeAsync(d_out, p->stream);
+    cudaFreeAsync(d_len, p->stream);
+    cudaStreamSynchronize(p->stream);
+    return rc;
+}
+
+// Global alignment of one pair with NO table: P column parts on one device (a checkpoint column every ~NW_CUDA_ALIGN_TILE
+// table columns, a checkpoint row per strip), filled one part after the other, then the tile-by-tile traceback.
+extern "C" int nw_cuda_align(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, const nw_scoring* scoring,
+                             int8_t* a1, int8_t* a2, int32_t* len, int32_t* score)
+{
+    if (!a1 || !a2 || !len) return fail(NW_ERR_ARG, "bad argument");
+    if (n1 < 0 || n2 < 0) return fail(NW_ERR_ARG, "negative sequence length");
+    Scoring sc;
+    int rc = parse_scoring(scoring, n1, n2, &sc);
+    if (rc) return rc;
+    if (sc.local) return fail(NW_ERR_UNSUPPORTED, "nw_cuda_align is a global alignment");
+    const int tile = std::max(64, env_int("NW_CUDA_ALIGN_TILE", 4096));
+    int P = (int)std::min<long long>(64, std::max<long long>(1, ((long long)n1 + tile - 1) / tile));
+    while (P > 1 && ((long long)n1 + 1) / P < 2) --P;
+    std::vector<nw_plan*> parts((size_t)P, nullptr);
+    nw_tuning tune;
+    memset(&tune, 0, sizeof tune);
+    Trace tr;
+    for (int g = 0; g < P && rc == NW_OK; ++g) {
+        rc = plan_create_internal(&parts[g], 0, n1, n2, NW_MODE_BOUNDARY, g, P, g == 0 ? nullptr : &tune, false, sc, true);
+        if (rc == NW_OK && g == 0) tune.rows_per_lane = parts[0]->R_req = parts[0]->R;     // every part: the same strip height
+    }
+    for (int g = 0; g + 1 < P && rc == NW_OK; ++g) rc = nw_plan_connect(parts[g], parts[g + 1]);
+    tr.mark("align: create parts");
+    for (int g = 0; g < P && rc == NW_OK; ++g) rc = nw_plan_upload(parts[g], s1, s2);
+    tr.mark("align: upload");
+    for (int g = 0; g < P && rc == NW_OK; ++g) {
+        // one device: part g+1 polls part g's right column, so it must not occupy the SMs before part g is done
+        if (g > 0 && cudaStreamWaitEvent(parts[g]->stream, parts[g - 1]->ev1, 0) != cudaSuccess) rc = fail(NW_ERR_CUDA, "cudaStreamWaitEvent failed");
+        if (rc == NW_OK) rc = nw_plan_run(parts[g]);
+    }
+    if (rc == NW_OK && score) rc = nw_plan_score(parts[(size_t)P - 1], score);
+    tr.mark("align: fill (all parts)");
+    if (rc == NW_OK) rc = nw_plans_traceback(parts.data(), P, a1, a2, len);
+    tr.mark("align: tile traceback");
+    char keep[512];
+    memcpy(keep, g_err, sizeof keep);
+    for (nw_plan* q : parts) nw_plan_destroy(q);
+    memcpy(g_err, keep, sizeof keep);
+    tr.mark("align: destroy");
+    return rc;
 }
 
 extern "C" int nw_plan_strip_info(nw_plan* p, int* nstrips, int* strip_rows, int* rows_per_lane, int* warps, int* ctas)
@@ -1554,6 +1724,7 @@ static std::vector<const void*> all_kernels()
     v.push_back((const void*)nw::nw_bidir_combine_kernel);
     v.push_back((const void*)nw::nw_reverse_kernel);
     v.push_back((const void*)nw::nw_traceback_kernel);
+    v.push_back((const void*)nw::nw_tile_trace_kernel);
     return v;
 }
 
@@ -1638,20 +1809,6 @@ extern "C" int nw_cuda_init(int device)
     return rc;
 }
 
-#include <chrono>
-namespace {
-struct Trace {      // NW_CUDA_TRACE=1: wall-clock phases of a one-shot call on stderr (stdout belongs to the driver)
-    bool on = env_int("NW_CUDA_TRACE", 0) != 0;
-    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-    void mark(const char* what)
-    {
-        if (!on) return;
-        const auto t1 = std::chrono::steady_clock::now();
-        fprintf(stderr, "[nw_cuda] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
-        t0 = t1;
-    }
-};
-}  // namespace
 
 static int run_pipeline(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int mode, int ngpus,
                         int32_t* table, int32_t* last_row, int32_t* last_col, int32_t* score, const Scoring& sc = Scoring(),
@@ -1681,7 +1838,7 @@ static int run_pipeline(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t 
         for (int g = 0; g < ngpus && rc == NW_OK; ++g) {
             rc = plan_create_internal(&cache[g], g, n1, n2, mode, g, ngpus, g == 0 ? nullptr : &tune,
                                       /*want_streamed=*/ngpus == 1 && mode == NW_MODE_FULL && table != nullptr, sc);
-            if (rc == NW_OK && g == 0) tune.rows_per_lane = cache[0]->R;     // all parts share the strip height
+            if (rc == NW_OK && g == 0 && ngpus > 1) tune.rows_per_lane = cache[0]->R_req = cache[0]->R;     // all parts share the strip height
         }
         for (int g = 0; g + 1 < ngpus && rc == NW_OK; ++g) rc = nw_plan_connect(cache[g], cache[g + 1]);
         if (rc != NW_OK) {

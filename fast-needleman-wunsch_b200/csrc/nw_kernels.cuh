@@ -542,36 +542,51 @@ __global__ void nw_presence_kernel64(const uint8_t* s, long long n, uint32_t* bi
 }
 
 // ---- traceback on a materialised table ----------------------------------------------------------------
-// One CTA walks back from H[n2][n1] to H[0][0].  The table lives in HBM, so a naive walk would pay one dependent global
+// One CTA walks back from a start cell.  The table lives in global memory, so a naive walk would pay one dependent global
 // load per step; instead the CTA stages a 64 x 64 window ending at the current cell in shared memory (coalesced row
 // segments), thread 0 walks inside it until it leaves, and the window is re-staged.  Rule per cell (the reference
-// defines none; this is the oracle's): diagonal if H[i][j] == H[i-1][j-1] + (s1[j-1]==s2[i-1]), else up if
-// H[i][j] == H[i-1][j] - 1, else left.  Output: the two gapped sequences REVERSED (gap = 0, README.md:8), and the length.
+// defines none; this is the oracle's): diagonal if H[i][j] == H[i-1][j-1] + (s1[j-1]==s2[i-1] ? match : mismatch), else up
+// if H[i][j] == H[i-1][j] + gap, else left.  Output: the two gapped sequences REVERSED (gap = 0, README.md:8).
+// TILE = false: the table is the whole table; walk to (0, 0), moves along row 0 / column 0 are forced.
+// TILE = true:  the table is one tile of it (row 0 / column 0 = its top / left boundary); stop on reaching either.
+// pos[0..2] (shared) = i, j, emitted; s1[j-1] / s2[i-1] are the letters of table column j / row i of THIS table.
 constexpr int TB_W = 64;
-__global__ void __launch_bounds__(256) nw_traceback_kernel(const int32_t* __restrict__ table, long long tpitch,
-                                                           const uint8_t* __restrict__ s1, const uint8_t* __restrict__ s2,
-                                                           int n1, int n2, uint8_t* out1, uint8_t* out2, int* out_len,
-                                                           int sc_match, int sc_mis, int sc_gap)
+struct WalkSmem {
+    int win[TB_W][TB_W + 1];
+    uint8_t c1[TB_W], c2[TB_W];
+};
+// cell accessors: a row-major table, and the phase-major scratch of the tile fill (see nw_tile_trace_kernel)
+struct RowMajorCells {
+    const int32_t* table;
+    long long tpitch;
+    static constexpr bool ROW_FASTEST = false;      // staging order that coalesces: columns fastest
+    __device__ __forceinline__ int operator()(int i, int j) const { return table[(long long)i * tpitch + j]; }
+};
+template <bool TILE, class Cells>
+__device__ __forceinline__ void walk_table(const Cells cells, const uint8_t* __restrict__ s1,
+                                           const uint8_t* __restrict__ s2, WalkSmem& w, volatile int* pos, uint8_t* out1,
+                                           uint8_t* out2, int sc_match, int sc_mis, int sc_gap)
 {
-    __shared__ int win[TB_W][TB_W + 1];
-    __shared__ uint8_t c1[TB_W], c2[TB_W];
-    __shared__ int pos[3];                 // i, j, emitted
-    if (threadIdx.x == 0) { pos[0] = n2; pos[1] = n1; pos[2] = 0; }
-    __syncthreads();
     for (;;) {
         const int i = pos[0], j = pos[1];
-        if (i == 0 && j == 0) break;
+        if (TILE ? (i == 0 || j == 0) : (i == 0 && j == 0)) break;
         const int wi0 = max(i - (TB_W - 1), 0), wj0 = max(j - (TB_W - 1), 0);     // window = rows wi0..i, cols wj0..j
         const int nr = i - wi0 + 1, nc = j - wj0 + 1;
-        for (int x = threadIdx.x; x < nr * TB_W; x += blockDim.x) {
-            const int r = x / TB_W, c = x - r * TB_W;
-            if (c < nc) win[r][c] = table[(long long)(wi0 + r) * tpitch + wj0 + c];
+        if (Cells::ROW_FASTEST) {
+            for (int x = threadIdx.x; x < nc * TB_W; x += blockDim.x) {
+                const int c = x / TB_W, r = x - c * TB_W;
+                if (r < nr) w.win[r][c] = cells(wi0 + r, wj0 + c);
+            }
+        } else {
+            for (int x = threadIdx.x; x < nr * TB_W; x += blockDim.x) {
+                const int r = x / TB_W, c = x - r * TB_W;
+                if (c < nc) w.win[r][c] = cells(wi0 + r, wj0 + c);
+            }
         }
         // s1[jj-1] for table columns jj = wj0+1..j  ->  c1[jj - wj0];  s2[ii-1] for rows ii = wi0+1..i -> c2[ii - wi0]
-        if (threadIdx.x < TB_W) {
-            const int c = threadIdx.x;
-            if (c >= 1 && c < nc) c1[c] = s1[wj0 + c - 1];
-            if (c >= 1 && c < nr) c2[c] = s2[wi0 + c - 1];
+        for (int c = threadIdx.x; c < TB_W; c += blockDim.x) {
+            if (c >= 1 && c < nc) w.c1[c] = s1[wj0 + c - 1];
+            if (c >= 1 && c < nr) w.c2[c] = s2[wi0 + c - 1];
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -579,22 +594,22 @@ __global__ void __launch_bounds__(256) nw_traceback_kernel(const int32_t* __rest
             // walk while the three neighbours are inside the window, or the move is forced by a table edge
             for (;;) {
                 const int gi = wi0 + a, gj = wj0 + b;
-                if (gi == 0 && gj == 0) break;
+                if (TILE ? (gi == 0 || gj == 0) : (gi == 0 && gj == 0)) break;
                 int move;                                      // 0 diag, 1 up, 2 left
                 if (gi == 0) move = 2;
                 else if (gj == 0) move = 1;
                 else {
                     if (a == 0 || b == 0) break;               // neighbours outside: re-stage the window
-                    const int h = win[a][b];
-                    if (h == win[a - 1][b - 1] + (c1[b] == c2[a] ? sc_match : sc_mis)) move = 0;
-                    else if (h == win[a - 1][b] + sc_gap) move = 1;
+                    const int h = w.win[a][b];
+                    if (h == w.win[a - 1][b - 1] + (w.c1[b] == w.c2[a] ? sc_match : sc_mis)) move = 0;
+                    else if (h == w.win[a - 1][b] + sc_gap) move = 1;
                     else move = 2;
                 }
                 if (move == 2 && gi == 0 && b == 0) break;     // need the previous window for the sequence byte
                 if (move == 1 && gj == 0 && a == 0) break;
-                if (move == 0) { out1[k] = c1[b]; out2[k] = c2[a]; --a; --b; }
-                else if (move == 1) { out1[k] = 0; out2[k] = c2[a]; --a; }
-                else { out1[k] = c1[b]; out2[k] = 0; --b; }
+                if (move == 0) { out1[k] = w.c1[b]; out2[k] = w.c2[a]; --a; --b; }
+                else if (move == 1) { out1[k] = 0; out2[k] = w.c2[a]; --a; }
+                else { out1[k] = w.c1[b]; out2[k] = 0; --b; }
                 ++k;
             }
             pos[0] = wi0 + a;
@@ -603,7 +618,180 @@ __global__ void __launch_bounds__(256) nw_traceback_kernel(const int32_t* __rest
         }
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(256) nw_traceback_kernel(const int32_t* __restrict__ table, long long tpitch,
+                                                           const uint8_t* __restrict__ s1, const uint8_t* __restrict__ s2,
+                                                           int n1, int n2, uint8_t* out1, uint8_t* out2, int* out_len,
+                                                           int sc_match, int sc_mis, int sc_gap)
+{
+    __shared__ WalkSmem w;
+    __shared__ int pos[3];                 // i, j, emitted
+    if (threadIdx.x == 0) { pos[0] = n2; pos[1] = n1; pos[2] = 0; }
+    __syncthreads();
+    walk_table<false>(RowMajorCells{table, tpitch}, s1, s2, w, pos, out1, out2, sc_match, sc_mis, sc_gap);
     if (threadIdx.x == 0) *out_len = pos[2];
+}
+
+// ---- traceback WITHOUT the table: replay one tile at a time from checkpoint rows and columns -----------------------------
+// After a boundary-mode fill of P column parts on one device, HBM holds a grid of checkpoints: the bottom row of every strip
+// of every part (brow, every 32*R table rows) and the left boundary column of every part > 0 (its halo mailbox, = the right
+// column of its neighbour).  The optimal path crosses every checkpoint row and column once.  One launch of this kernel
+// handles the tile the current cell (i, j) lies in -- rows (i_top, i] of its strip, columns (j_left, j] of its part:
+//   1. fill the tile in H form from its exact top row and left column (blocked wavefront: thread r owns tile row r+1 and
+//      trails thread r-1 by one block of TT_B columns; neighbours exchange blocks through shared memory, one
+//      __syncthreads per block step) into a scratch table -- any alphabet, any linear scoring.  The scratch is
+//      PHASE-major (cell (r+1, c+1) at [((c / TT_B + r) * TT_B + c % TT_B) * rpitch + r]): at any instant the threads work on
+//      different columns, and this is the layout in which their stores coalesce (row- or column-major scratch costs 32
+//      cache lines per store instruction and was 7x slower);
+//   2. walk back inside the scratch table (walk_table<true>) until the path reaches the tile's top row or left column;
+//   3. leave the new (i, j) and the number of emitted columns in `state` for the next launch.
+// Along table row 0 / column 0 the rest of the path is forced (gaps) and is emitted directly.  The host enqueues
+// nstrips + nparts + 1 launches (a monotone path cannot visit more tiles); launches after the end do nothing.
+struct TracePart {
+    const int2* brow;       // this part's boundary rows: brow[s * pitch + c], c = 0..ncols (local table column)
+    long long pitch;
+    const int2* halo;       // tagged left boundary column (G form) indexed by table row, or nullptr for part 0
+    int jstart, ncols;      // table column of the left boundary column; interior columns
+};
+struct TraceParams {
+    const TracePart* parts;
+    int nparts;
+    const uint8_t* s1;      // the WHOLE s1 (n1 bytes) and s2
+    const uint8_t* s2;
+    int n1, n2, nstrips, strip_rows, pad_top;
+    int sc_match, sc_mis, sc_gap;
+    int32_t* scratch;       // top row (spitch ints), left column (spitch ints), then the phase-major cells
+    long long spitch;       // >= widest part + 1 and >= strip_rows + 1
+    int rpitch;             // threads per CTA (= strip_rows)
+    int* state;             // i, j, emitted, error, then statistics: tiles, fill kcycles, walk kcycles, phases
+    uint8_t* out1;
+    uint8_t* out2;
+};
+constexpr int TT_B = 8;            // columns per thread per block step
+constexpr int TT_MAX_ROWS = 512;   // strip rows (threads)
+
+struct TileCells {
+    const int32_t* top;      // tile row 0
+    const int32_t* leftc;    // tile column 0
+    const int32_t* cells;
+    int rpitch;
+    static constexpr bool ROW_FASTEST = true;
+    __device__ __forceinline__ int operator()(int a, int b) const
+    {
+        if (a == 0) return top[b];
+        if (b == 0) return leftc[a];
+        const int r = a - 1, c = b - 1;
+        return cells[(long long)(((c / TT_B) + r) * TT_B + (c % TT_B)) * rpitch + r];
+    }
+};
+
+__global__ void __launch_bounds__(TT_MAX_ROWS) nw_tile_trace_kernel(const TraceParams p)
+{
+    __shared__ union {
+        int up[2][TT_B][TT_MAX_ROWS];      // fill: the blocks handed from row to row (row index last: no bank conflicts)
+        WalkSmem walk;                     // then the walker's window
+    } sm;
+    __shared__ int pos[3];
+    const int tid = threadIdx.x;
+    const int i = p.state[0], j = p.state[1], k0 = p.state[2];
+    if ((i == 0 && j == 0) || p.state[3] != 0) return;
+    const int g = p.sc_gap;
+    if (i == 0 || j == 0) {      // forced: only gaps are left
+        const int n = i + j;
+        for (int x = tid; x < n; x += blockDim.x) {
+            p.out1[k0 + x] = (i == 0) ? p.s1[j - 1 - x] : 0;
+            p.out2[k0 + x] = (i == 0) ? 0 : p.s2[i - 1 - x];
+        }
+        __syncthreads();
+        if (tid == 0) { p.state[0] = 0; p.state[1] = 0; p.state[2] = k0 + n; }
+        return;
+    }
+    // the tile of (i, j)
+    const int s = (i - 1 + p.pad_top) / p.strip_rows;
+    int part = 0;
+    while (part + 1 < p.nparts && p.parts[part + 1].jstart < j) ++part;
+    const TracePart tp = p.parts[part];
+    const int i_top = max(s * p.strip_rows - p.pad_top, 0);
+    const int nr = i - i_top, jl = tp.jstart, wd = j - jl;       // tile rows 1..nr, columns 1..wd (0 = boundaries)
+    if (nr > blockDim.x || wd + 1 > p.spitch || nr + 1 > p.spitch || wd > tp.ncols || (int)blockDim.x != p.rpitch) {
+        if (tid == 0) p.state[3] = 1;
+        return;
+    }
+    int32_t* const top = p.scratch;
+    int32_t* const leftc = p.scratch + p.spitch;
+    int32_t* const U = p.scratch + 2 * p.spitch;
+    const int rp = p.rpitch;
+    // top boundary row (H form): the init row of the table, or the checkpoint row of the strip above
+    const int2* trow = (i_top > 0) ? tp.brow + (long long)(s - 1) * tp.pitch : nullptr;
+    for (int c = tid; c <= wd; c += blockDim.x) top[c] = (trow ? trow[c].y : 0) + g * (i_top + jl + c);
+    // left boundary column: the init column, or the neighbour's right column
+    for (int a = tid; a <= nr; a += blockDim.x)
+        leftc[a] = (a == 0) ? (trow ? trow[0].y : 0) + g * (i_top + jl)
+                            : (tp.halo ? tp.halo[i_top + a].y : 0) + g * (i_top + a + jl);
+    __syncthreads();
+
+    const long long clk0 = clock64();
+    const int r = tid;
+    const bool rowok = r < nr;
+    const int nq = (wd + TT_B - 1) / TT_B;
+    const uint8_t b2 = rowok ? p.s2[i_top + r] : 0;
+    int left = rowok ? leftc[r + 1] : 0;
+    int diag = rowok ? leftc[r] : 0;
+    const uint8_t* __restrict__ s1 = p.s1 + jl;                 // letter of tile column c (1-based) = s1[c - 1]
+    const int nsteps = nq + nr - 1;
+    int upn[TT_B];                      // row 0 reads the top boundary row from global memory: one block ahead
+#pragma unroll
+    for (int x = 0; x < TT_B; ++x) upn[x] = (r == 0 && x < wd) ? top[x + 1] : 0;
+    for (int t = 0; t < nsteps; ++t) {
+        const int q = t - r;
+        if (rowok && q >= 0 && q < nq) {
+            const int c0 = q * TT_B;
+            int up[TT_B];
+            if (r == 0) {
+#pragma unroll
+                for (int x = 0; x < TT_B; ++x) {
+                    up[x] = upn[x];
+                    upn[x] = (c0 + TT_B + x < wd) ? top[c0 + TT_B + x + 1] : 0;
+                }
+            } else {
+#pragma unroll
+                for (int x = 0; x < TT_B; ++x) up[x] = sm.up[(t - 1) & 1][x][r - 1];
+            }
+            uint8_t cs[TT_B];
+#pragma unroll
+            for (int x = 0; x < TT_B; ++x) cs[x] = (c0 + x < wd) ? s1[c0 + x] : 0;
+            int32_t* const Ut = U + (long long)t * TT_B * rp + r;      // this thread's cells of this phase: coalesced over r
+#pragma unroll
+            for (int x = 0; x < TT_B; ++x) {
+                if (c0 + x < wd) {
+                    const int sub = (cs[x] == b2) ? p.sc_match : p.sc_mis;
+                    const int h = max(max(diag + sub, up[x] + g), left + g);
+                    Ut[(long long)x * rp] = h;
+                    diag = up[x];
+                    left = h;
+                    up[x] = h;
+                }
+            }
+#pragma unroll
+            for (int x = 0; x < TT_B; ++x) sm.up[t & 1][x][r] = up[x];
+        }
+        __syncthreads();
+    }
+    // walk back inside the tile
+    const long long clk1 = clock64();
+    if (tid == 0) { pos[0] = nr; pos[1] = wd; pos[2] = k0; }
+    __syncthreads();
+    walk_table<true>(TileCells{top, leftc, U, rp}, s1, p.s2 + i_top, sm.walk, pos, p.out1, p.out2, p.sc_match, p.sc_mis, p.sc_gap);
+    if (tid == 0) {
+        p.state[0] = i_top + pos[0];
+        p.state[1] = jl + pos[1];
+        p.state[2] = pos[2];
+        p.state[4] += 1;
+        p.state[5] += (int)((clk1 - clk0) >> 10);
+        p.state[6] += (int)((clock64() - clk1) >> 10);
+        p.state[7] += nsteps;
+    }
 }
 
 // integer / DPX pipe rate: 8 independent VIADDMNMX chains per thread (roofline denominator)

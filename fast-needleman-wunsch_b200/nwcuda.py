@@ -26,7 +26,7 @@ EXPORTS = [
     "nw_batch_create", "nw_batch_destroy", "nw_batch_upload", "nw_batch_upload_device", "nw_batch_run",
     "nw_batch_sync", "nw_batch_time", "nw_batch_scores", "nw_cuda_dpx_peak",
     "nw_cuda_fill_scored", "nw_cuda_score_scored", "nw_cuda_batch_scores_scored", "nw_plan_create_scored", "nw_plan_best",
-    "nw_batch_set_scoring",
+    "nw_batch_set_scoring", "nw_plans_traceback", "nw_cuda_align",
 ]
 
 
@@ -99,6 +99,8 @@ def lib():
                                       C.POINTER(Scoring)],
             "nw_plan_best": [vp, vp, vp, vp],
             "nw_batch_set_scoring": [vp, C.POINTER(Scoring)],
+            "nw_plans_traceback": [C.POINTER(vp), C.c_int, vp, vp, ip],
+            "nw_cuda_align": [vp, i32, vp, i32, C.POINTER(Scoring), vp, vp, ip, ip],
         }
         for name, args in sigs.items():
             f = getattr(L, name)
@@ -199,6 +201,28 @@ def boundaries(s1, s2):
     out = C.c_int32()
     _ck(lib().nw_cuda_boundaries(_ptr(s1), s1.size, _ptr(s2), s2.size, row.ctypes.data, col.ctypes.data, C.byref(out)))
     return row, col, out.value
+
+
+def align(s1, s2, scoring=None):
+    """(a1, a2, score): the gapped s1 and s2 (gap = 0, README.md:8) of the optimal global alignment, computed without a
+    table (checkpoint rows and columns + tile replay, nw_cuda_align)."""
+    s1, s2 = _seq(s1), _seq(s2)
+    cap = s1.size + s2.size + 1
+    a1, a2 = np.empty(cap, dtype=np.int8), np.empty(cap, dtype=np.int8)
+    n, sc = C.c_int(), C.c_int()
+    _ck(lib().nw_cuda_align(_ptr(s1), s1.size, _ptr(s2), s2.size, _scoring(scoring), a1.ctypes.data, a2.ctypes.data,
+                            C.byref(n), C.byref(sc)))
+    return a1[:n.value].copy(), a2[:n.value].copy(), sc.value
+
+
+def plans_traceback(plans):
+    """Traceback over the connected parts of a pipeline on one device (nw_plans_traceback)."""
+    cap = plans[0].n1 + plans[0].n2 + 1
+    a1, a2 = np.empty(cap, dtype=np.int8), np.empty(cap, dtype=np.int8)
+    n = C.c_int()
+    arr = (C.c_void_p * len(plans))(*[p._h for p in plans])
+    _ck(lib().nw_plans_traceback(arr, len(plans), a1.ctypes.data, a2.ctypes.data, C.byref(n)))
+    return a1[:n.value].copy(), a2[:n.value].copy()
 
 
 def batch_scores(S1, S2, device=0, scoring=None):

@@ -177,12 +177,21 @@ int nw_plan_last_col(nw_plan* p, int32_t* last_col /* n2+1 H values of this part
 int nw_plan_table_to_host(nw_plan* p, int32_t* table);
 /* Full mode only: device pointer and row pitch (elements) of this part's table (rows 0..n2, local columns). */
 int nw_plan_table_device(nw_plan* p, int32_t** d_table, int64_t* pitch);
-/* Alignment from the filled table (full-table, single-part plans; the reference defines the gap code and a printer --
- * README.md:8, src/common/helper.cpp:27-34 -- but never produces an alignment).  Walks back on the DEVICE-resident
- * table from H[n2][n1] to H[0][0]: diagonal if H[i][j] == H[i-1][j-1] + (s1[j-1]==s2[i-1]), else up if
- * H[i][j] == H[i-1][j] - 1, else left.  a1 / a2 (HOST, capacity n1+n2 each) receive the gapped s1 / s2 left to right,
- * gap = 0; *len their common length. */
+/* Alignment (the reference defines the gap code and a printer -- README.md:8, src/common/helper.cpp:27-34 -- but never
+ * produces an alignment).  Walks back from H[n2][n1] to H[0][0]: diagonal if H[i][j] == H[i-1][j-1] + (s1[j-1]==s2[i-1] ?
+ * match : mismatch), else up if H[i][j] == H[i-1][j] + gap, else left.  a1 / a2 (HOST, capacity n1+n2 each) receive the
+ * gapped s1 / s2 left to right, gap = 0; *len their common length.
+ *   full-table plan (single part, table resident): walks the materialised table;
+ *   boundary-mode plan: NO table -- the path is recovered tile by tile from the strip boundary rows the fill left in HBM
+ *   (every tile between two checkpoint rows is recomputed from its exact top row and left column, then walked).
+ * nw_plans_traceback does the same for the connected parts 0..nparts-1 of a column-strip pipeline on ONE device that
+ * have all run the same fill: their halo columns are checkpoint columns, so a tile is strip_rows x (part width). */
 int nw_plan_traceback(nw_plan* p, int8_t* a1, int8_t* a2, int32_t* len);
+int nw_plans_traceback(nw_plan* const* parts, int nparts, int8_t* a1, int8_t* a2, int32_t* len);
+/* One-shot, HOST buffers, no table anywhere: column parts of ~NW_CUDA_ALIGN_TILE (default 4096) columns on device 0,
+ * filled one after the other, then nw_plans_traceback.  scoring may be NULL (global alignment only); score may be NULL. */
+int nw_cuda_align(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, const nw_scoring* scoring,
+                  int8_t* a1, int8_t* a2, int32_t* len, int32_t* score);
 /* Strip boundary rows kept in HBM (checkpoint rows): number of strips, rows per strip and, per strip k, the
  * H values of table row  n2 - (nstrips-1-k)*strip_rows  copied to HOST (ncols of this part). */
 int nw_plan_strip_info(nw_plan* p, int* nstrips, int* strip_rows, int* rows_per_lane, int* warps, int* ctas);
