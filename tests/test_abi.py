@@ -13,7 +13,7 @@ from conftest import ROOT
 def declared_symbols():
     src = open(os.path.join(ROOT, "include", "nw_cuda.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(nw_(?:cuda|plan|batch)_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(nw_(?:cuda|plans?|batch)_\w+)\s*\(", src)))
 
 
 def test_header_declares_expected_surface(nw):
