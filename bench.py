@@ -395,6 +395,90 @@ def time_pair(nw, name, mode, steps, device, cpu_pairs):
     return out
 
 
+TALL = {"n1": 262144, "n2": 1048576, "seed": 20261018, "score": -524289}     # score: oracle/nw_oracle.c on the host (666 s, one core)
+
+
+def tall_pair(nw, torch, dist, pipeline, world, rank, device, steps=3):
+    """Secondary measurement at every N: a THROUGHPUT-bound single pair (4096 strips of 256 rows against 592 warp slots per
+    GPU, so every scheduler always has a strip to work on), column strips over the N ranks exactly like the headline pair.
+    This is the regime in which the mpi-vert decomposition (src/mpi/mpi-vert.cpp:17-105) pays: the headline pair is
+    bound by its critical path on one GPU already."""
+    n1, n2 = TALL["n1"], TALL["n2"]
+    rng = np.random.default_rng(TALL["seed"])
+    s1 = rng.integers(1, 5, size=n1, dtype=np.int8)
+    s2 = rng.integers(1, 5, size=n2, dtype=np.int8)
+    plan = nw.Plan(n1, n2, device=device, part=rank, nparts=world, rows_per_lane=8)
+    try:
+        if world > 1:
+            pipeline.exchange_mailboxes(dist, plan, rank, world)
+        plan.upload(s1, s2)
+        plan.sync()
+
+        def step():
+            plan.run()
+            plan.sync()
+            if world > 1:
+                dist.barrier()
+            return plan.last_ms()
+        step()
+        ms = [step() for _ in range(steps)]
+        t = torch.tensor(ms, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.mean().item())
+        score = plan.score() if rank == world - 1 else None
+        if world > 1:
+            box = [score]
+            dist.broadcast_object_list(box, src=world - 1)
+            score = box[0]
+        info = plan.strip_info()
+    finally:
+        plan.close()
+    if TALL["score"] is not None and score != TALL["score"]:
+        raise SystemExit(f"bench: tall pair score {score} != oracle {TALL['score']}")
+    return {"workload": f"tall synthetic pair ({n1} x {n2} = {n1 * n2} cells, iid bases, seed {TALL['seed']}), boundary-only mode",
+            "parallelism": f"column strips x{world}" if world > 1 else "single GPU", "nstrips": info["nstrips"],
+            "ms_per_fill": ms, "gcups": n1 * n2 / ms / 1e6, "steps": steps, "score": score,
+            "score_checked_against": "CPU oracle (two-row restatement of serial.cpp)" if TALL["score"] is not None else None,
+            "what": "latency of one fill, max over ranks; throughput-bound (more strips than resident warps), so column "
+                    "strips over N GPUs shorten it"}
+
+
+def widened_numbers(nw, device):
+    """SURVEY.md 8(f) rows measured beside the headline (one GPU): other scoring triples through the same kernels,
+    Smith-Waterman, and the alignment output without a table."""
+    out = []
+    s1, s2, _ = load_pair("64gb")
+    for sc in ((2, -1, -2), (5, -4, -3)):
+        with nw.Plan(s1.size, s2.size, device=device, scoring=sc) as p:
+            p.upload(s1, s2)
+            p.time(1)
+            ms = p.time(3)
+            out.append({"workload": f"64gb pair, boundary-only mode, scoring match/mismatch/gap = {sc}", "ms_per_fill": ms,
+                        "gcups": s1.size * s2.size / ms / 1e6, "score": p.score()})
+    a, b, _ = load_pair("mid")
+    sc = (2, -1, -2, 1)
+    with nw.Plan(a.size, b.size, device=device, scoring=sc) as p:
+        p.upload(a, b)
+        p.time(1)
+        ms = p.time(3)
+        out.append({"workload": f"mid pair, Smith-Waterman (local alignment), scoring {sc[:3]}: best cell + position",
+                    "ms_per_fill": ms, "gcups": a.size * b.size / ms / 1e6, "best": list(p.best())})
+    for nm in ("2gb", "64gb"):
+        x, y, _ = load_pair(nm)
+        nw.align(x, y)
+        t0 = time.perf_counter()
+        a1, a2, score = nw.align(x, y)
+        ms = (time.perf_counter() - t0) * 1e3
+        ok = bool(np.array_equal(a1[a1 != 0], x) and np.array_equal(a2[a2 != 0], y) and
+                  int(np.where((a1 == 0) | (a2 == 0), -1, (a1 == a2).astype(np.int64)).sum()) == score)
+        out.append({"workload": f"{nm} pair, global alignment WITHOUT a table (nw_cuda_align: checkpoint rows + columns, tile "
+                                "replay), host sequences in, gapped sequences out", "wall_ms": ms, "columns": int(a1.size),
+                    "score": score, "score_matches_golden": score == GOLDEN_SCORES.get(nm),
+                    "alignment_spells_both_sequences_and_scores": ok})
+    return out
+
+
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -555,6 +639,15 @@ def gpu_arm(args):
         dist.all_reduce(t)
         launches = int(t.item())
 
+    tall = None
+    if not args.no_configs and not full:
+        try:
+            tall = tall_pair(nw, torch, dist, pipeline, world, rank, device)
+        except SystemExit:
+            raise
+        except Exception as e:          # (every rank fails alike: sizes and memory are the same)
+            tall = {"workload": "tall synthetic pair", "error": str(e)[:200]}
+
     if rank == 0:
         peaks = measured_peaks()
         dpx_g, dpx_mhz = nw.dpx_peak(device)                      # measured integer/DPX pipe rate of THIS GPU
@@ -596,6 +689,10 @@ def gpu_arm(args):
                 configs.append(batch_numbers(nw, torch, 200000, 3, device)[0])
             except Exception as e:
                 configs.append({"workload": "batch", "error": str(e)[:200]})
+            try:
+                configs.extend(widened_numbers(nw, device))
+            except Exception as e:
+                configs.append({"workload": "scoring / local / align", "error": str(e)[:200]})
             # fresh-process runs of the reference's driver around the plug-in (pairs whose host table is quick to
             # allocate and touch; the 64gb pair's 64 GB table takes the driver ~30 s per run: profiles/r02_driver_cold.log)
             cold = {"2gb_boundary": cold_driver_runs("2gb", "boundary"), "2gb_full": cold_driver_runs("2gb", "full", runs=3),
@@ -623,6 +720,8 @@ def gpu_arm(args):
                                          "what": "K fills enqueued back to back without a sync in between (for N > 1 "
                                                  "consecutive fills overlap across the GPUs); NOT the latency of one fill"},
                 "gpu_launches": launches, "roofline": roof}
+        if tall is not None:
+            line["throughput_bound_pair"] = tall
         if score_only is not None:
             line["score_only"] = score_only
         if cold is not None:
