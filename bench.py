@@ -588,6 +588,25 @@ def gpu_arm(args):
                                   "H[n2][n1] = max_j F[m][j] + B[m][j]; same number of cell updates, bit-exact score",
                           "launches_per_step": splan.launches_per_run()}
 
+    # ---- score-only mode with one half per GPU (N >= 2; rank 0 drives devices 0 and 1 in-process) --------------------------
+    if world >= 2 and not full:
+        barrier()
+        if rank == 0:
+            nw.init(1)
+            with nw.Plan(n1, n2, mode=nw.NW_MODE_SCORE, device=0, part=0, nparts=2) as splan:
+                splan.upload(s1, s2)
+                splan.time(max(1, min(args.warmup, 3)))
+                so_ms = splan.time(args.steps)
+                if splan.score() != score:
+                    raise SystemExit(f"bench: two-GPU score-mode score {splan.score()} != {score}")
+                score_only = {"value": cells / so_ms / 1e6, "unit": "GCUPS", "ms_per_step": so_ms, "gpus_used": 2,
+                              "mode": "NW_MODE_SCORE, part 0 of 2: the forward half of the table on GPU 0, the reversed half "
+                                      "on GPU 1, cut along a staircase (every strip sweeps only its side of it, so the strips' "
+                                      "start-up lag overlaps their shorter sweeps); no traffic between the GPUs until the "
+                                      "combine kernel reads the second half's boundary rows through peer access",
+                              "launches_per_step": splan.launches_per_run()}
+        barrier()
+
     # ---- end to end: HOST sequences in, fill, result out, every step -----------------------------------------------------
     table = None
     if world == 1:
@@ -605,7 +624,7 @@ def gpu_arm(args):
             e2e_path = ("nw_cuda_fill_ex(host s1, host s2, host table, NW_MODE_BOUNDARY, 1) per step -- the call "
                         "csrc/cuda.cpp makes for the reference's driver; score-only mode (NW_MODE_SCORE) inside, plan cached "
                         "across calls (warm)")
-    else:
+    elif full:
         def e2e_step():
             plan.upload(s1, s2)                # H2D of this part's slice + all of s2, operand encoding
             plan.run()
@@ -613,6 +632,20 @@ def gpu_arm(args):
             barrier()
             return r
         e2e_path = "nw_plan_upload(host s1, s2) + nw_plan_run + nw_plan_score per step on every rank (one process per GPU)"
+    else:
+        # the plug-in call of the reference-side binding with NW_CUDA_GPUS = N, made by rank 0 (one process drives the
+        # devices, like cuda.e does); the other ranks wait at the barrier
+        for d in range(min(world, 2)):
+            if rank == 0:
+                nw.init(d)
+
+        def e2e_step():
+            r = plugin_boundary_call(nw, s1, s2, ngpus=world) if rank == 0 else None
+            barrier()
+            return r
+        e2e_path = (f"nw_cuda_fill_ex(host s1, host s2, host table, NW_MODE_BOUNDARY, {world}) per step from rank 0 -- the call "
+                    "csrc/cuda.cpp makes with NW_CUDA_GPUS=N: score-only mode with one half of the table on each of the first "
+                    "two GPUs (cut along a staircase); plan cached across calls (warm)")
     barrier()
     for _ in range(min(args.warmup, 3)):
         e2e_step()
@@ -623,14 +656,15 @@ def gpu_arm(args):
         r = e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    if rank == world - 1 and expect is not None and r != expect:
+    e2e_rank = world - 1 if (world == 1 or full) else 0
+    if rank == e2e_rank and expect is not None and r != expect:
         raise SystemExit(f"bench: end-to-end score {r} != golden {expect}")
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_gcups = cells * args.steps / e2e_s / 1e9
-    h2d = int(plan.ncols + n2) * world if world > 1 else int(n1 + n2)
+    h2d = int(plan.ncols + n2) * world if (world > 1 and full) else int(n1 + n2) * min(world, 2)
     d2h = 4 + (int(table.nbytes) if table is not None else 0)
 
     launches = plan.launches_per_run() * args.steps
@@ -711,8 +745,9 @@ def gpu_arm(args):
                            "timing": "every step = one fill timed alone by CUDA events on the plan's stream, then a stream "
                                      "sync (and a barrier for N > 1): ms_per_step is the latency of one fill, max over ranks",
                            "modes": "value = one forward fill that keeps every strip boundary row and the last row/column "
-                                    "(NW_MODE_BOUNDARY plan); score_only = the score-only algorithm (NW_MODE_SCORE), kernel "
-                                    "only; e2e = the plug-in call, which uses NW_MODE_SCORE inside on one GPU"},
+                                    "(NW_MODE_BOUNDARY plan; column strips for N > 1); score_only = the score-only algorithm "
+                                    "(NW_MODE_SCORE; one half per GPU on two GPUs for N >= 2), kernel only; e2e = the plug-in "
+                                    "call, which uses NW_MODE_SCORE inside"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3 / args.steps, "path": e2e_path},

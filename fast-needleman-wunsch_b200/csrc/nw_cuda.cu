@@ -140,13 +140,13 @@ StripKernel strip16_kernel(int regs)
     }
 }
 
-StripKernel strip16l2_kernel(int regs)
+StripKernel strip16l2_kernel(int regs, bool stair = false)
 {
     switch (regs) {
-    case 1: return nw::nw_strip16l2_kernel<1>;
-    case 2: return nw::nw_strip16l2_kernel<2>;
-    case 4: return nw::nw_strip16l2_kernel<4>;
-    case 8: return nw::nw_strip16l2_kernel<8>;
+    case 1: return stair ? nw::nw_strip16l2_kernel<1, true> : nw::nw_strip16l2_kernel<1, false>;
+    case 2: return stair ? nw::nw_strip16l2_kernel<2, true> : nw::nw_strip16l2_kernel<2, false>;
+    case 4: return stair ? nw::nw_strip16l2_kernel<4, true> : nw::nw_strip16l2_kernel<4, false>;
+    case 8: return stair ? nw::nw_strip16l2_kernel<8, true> : nw::nw_strip16l2_kernel<8, false>;
     default: return nullptr;
     }
 }
@@ -324,6 +324,17 @@ struct nw_plan {
     int split = 0;                   // rows of the top half
     bool swapped = false;            // score mode sweeps along the SHORTER sequence (the score is symmetric in s1, s2)
     cudaEvent_t join_ev = nullptr;
+    // score mode along a staircase: both sub-plans span all rows; strip s of the forward one sweeps
+    // widths[s] columns, strip t of the reversed one the rest.  stair_half: 0 = not a half, 1 = forward, 2 = reversed (padding
+    // rows at the bottom, so that both halves share their strip boundaries)
+    uint8_t code[256];               // letter codes of the most recent upload (four-letter paths)
+    int stair_half = 0;
+    int dev2 = -1;                   // (on the parent) device of the second half: the same one, or a second GPU
+    bool stair = false;              // (on the parent) the sub-plans were built for the staircase
+    int* d_widths = nullptr;
+    uint32_t* d_tails = nullptr;
+    size_t widths_n = 0;
+    Scoring scoring_of() const { Scoring sc; sc.match = sc_match; sc.mismatch = sc_mis; sc.gap = sc_gap; sc.local = local ? 1 : 0; return sc; }
     // scoring (nw_scoring; default = the reference's macros, src/common/needleman-wunsch.hpp:11-13)
     int sc_match = 1, sc_mis = 0, sc_gap = -1;
     bool local = false;              // Smith-Waterman (nw_local.cuh)
@@ -453,11 +464,12 @@ extern "C" int nw_plan_destroy(nw_plan* p)
     if (p->sub[0]) nw_plan_destroy(p->sub[0]);
     if (p->sub[1]) nw_plan_destroy(p->sub[1]);
     if (p->join_ev) cudaEventDestroy(p->join_ev);
+    cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->ipc_mailbox) cudaIpcCloseMemHandle(p->ipc_mailbox);
     void* bufs[] = {p->d_s1, p->d_s2, p->d_wq, p->d_rsel, p->d_bitmap, p->d_brow, p->d_rcol_local, p->d_table,
                     p->d_dump, p->d_snap, p->d_last_row, p->d_last_col, p->d_score, p->d_tmp_row, p->d_rev, p->d_times,
-                    p->d_local_best};
+                    p->d_local_best, p->d_widths, p->d_tails};
     for (void* b : bufs)
         if (b) cudaFreeAsync(b, p->stream ? p->stream : (cudaStream_t)0);      // back into the device's pool
     if (p->d_mailbox && p->mailbox_pooled) cudaFreeAsync(p->d_mailbox, p->stream ? p->stream : (cudaStream_t)0);
@@ -541,7 +553,7 @@ static int plan_pick_kernel(nw_plan* p)
     p->R = R;
     p->warps = p->warps_req ? p->warps_req : (p->packed ? 4 : 8);
     p->nstrips = (int)(((long long)p->n2 + 32LL * R - 1) / (32LL * R));
-    p->pad_top = p->nstrips * 32 * R - p->n2;
+    p->pad_top = (p->stair_half == 2) ? 0 : p->nstrips * 32 * R - p->n2;
     const size_t rsel_words = (size_t)std::max(p->nstrips * 32 * R, 2);      // (packed: R/2 registers x 2 words each)
     const size_t brow_words = (size_t)p->pitch * (size_t)std::max(p->nstrips, 1) + 2;
     if (rsel_words > p->rsel_words) {
@@ -566,13 +578,13 @@ static int plan_pick_kernel(nw_plan* p)
     // boundary mode: the lag-2 schedule (nw_lag2.cuh); NW_CUDA_LAG2=0 selects the one-column skew of nw_packed.cuh, which
     // full-table mode always uses (its pass 2 replays tiles with the same schedule)
     p->lag2 = p->packed && p->mode == NW_MODE_BOUNDARY && env_int("NW_CUDA_LAG2", 1) != 0;
-    p->ws = p->lag2 && env_int("NW_CUDA_WS", 0) != 0 && p->warps <= 8;   // opt-in: measured slower in a chain
+    p->ws = p->lag2 && env_int("NW_CUDA_WS", 0) != 0 && p->warps <= 8 && p->stair_half == 0;   // opt-in: measured slower in a chain
     p->threads = p->warps * (p->ws ? 64 : 32);
     if (p->ws) {
         p->kernel = strip16ws_kernel(R / 2);
         p->smem = sizeof(uint32_t) * nw::WS_SMEM_WORDS_PER_PAIR * (size_t)p->warps;
     } else if (p->lag2) {
-        p->kernel = strip16l2_kernel(R / 2);
+        p->kernel = strip16l2_kernel(R / 2, p->stair_half != 0);
         p->smem = sizeof(uint32_t) * nw::L2_SMEM_WORDS_PER_WARP * (size_t)p->warps;
     } else if (p->packed) {
         p->kernel = strip16_kernel(R / 2);
@@ -661,7 +673,10 @@ static int plan_pick_kernel(nw_plan* p)
 }
 
 static int plan_create_internal(nw_plan** out, int device, int32_t n1, int32_t n2, int mode, int part, int nparts,
-                                const nw_tuning* tuning, bool want_streamed, const Scoring& sc, bool same_device_pipeline = false);
+                                const nw_tuning* tuning, bool want_streamed, const Scoring& sc, bool same_device_pipeline = false,
+                                int stair_half = 0);
+static int score_build(nw_plan* q, bool stair);
+static bool score_can_stair(const nw_plan* q, const bool seen[256]);
 
 extern "C" int nw_plan_create(nw_plan** out, int device, int32_t n1, int32_t n2, int mode, int part, int nparts,
                               const nw_tuning* tuning)
@@ -681,7 +696,8 @@ extern "C" int nw_plan_create_scored(nw_plan** out, int device, int32_t n1, int3
 }
 
 static int plan_create_internal(nw_plan** out, int device, int32_t n1, int32_t n2, int mode, int part, int nparts,
-                                const nw_tuning* tuning, bool want_streamed, const Scoring& sc, bool same_device_pipeline)
+                                const nw_tuning* tuning, bool want_streamed, const Scoring& sc, bool same_device_pipeline,
+                                int stair_half)
 {
     if (!out) return fail(NW_ERR_ARG, "out is NULL");
     *out = nullptr;
@@ -691,23 +707,53 @@ static int plan_create_internal(nw_plan** out, int device, int32_t n1, int32_t n
         if (mode == NW_MODE_SCORE) mode = NW_MODE_BOUNDARY;      // the best cell can be anywhere: no meeting in the middle
     }
     if (mode == NW_MODE_SCORE) {
-        if (nparts != 1 || part != 0) return fail(NW_ERR_UNSUPPORTED, "score mode is a single-device mode");
+        // nparts = 2: the two halves on devices `device` and `device + 1` (their strips never talk to each other; the
+        // combine kernel reads the second half's boundary rows and columns through peer access)
+        if ((nparts != 1 && nparts != 2) || part != 0) return fail(NW_ERR_UNSUPPORTED, "score mode runs on one device, or on two (part 0 of 2)");
         int rc0 = ensure_device(device);
         if (rc0) return rc0;
+        const int dev2 = (nparts == 2) ? device + 1 : device;
+        if (dev2 != device) {
+            rc0 = ensure_device(dev2);
+            if (rc0) return rc0;
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, device, dev2));
+            if (!can) return fail(NW_ERR_UNSUPPORTED, "device %d cannot access device %d", device, dev2);
+            CK(cudaSetDevice(device));
+            cudaError_t e = cudaDeviceEnablePeerAccess(dev2, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+            cudaGetLastError();
+            cudaMemAccessDesc desc;
+            memset(&desc, 0, sizeof desc);
+            desc.location.type = cudaMemLocationTypeDevice;
+            desc.location.id = device;
+            desc.flags = cudaMemAccessFlagsProtReadWrite;
+            CK(cudaMemPoolSetAccess(g_dev[dev2].pool, &desc, 1));       // the second half's buffers come from this pool
+        }
         nw_plan* q = new (std::nothrow) nw_plan;
         if (!q) return fail(NW_ERR_CUDA, "out of host memory");
         // a column costs a full step of the critical path, a row only 1/256 of a strip's start-up lag: columns = shorter one
         q->swapped = n1 > n2 && !env_int("NW_CUDA_NO_SWAP", 0);
         if (q->swapped) std::swap(n1, n2);
         q->device = device; q->n1 = n1; q->n2 = n2; q->mode = mode;
+        q->dev2 = dev2;
         q->sc_match = sc.match; q->sc_mis = sc.mismatch; q->sc_gap = sc.gap;
+        q->R_req = tuning ? tuning->rows_per_lane : 0;
+        q->warps_req = tuning ? tuning->warps_per_cta : 0;
+        q->ctas_req = tuning ? tuning->ctas : 0;
         q->split = n2 / 2;
-        rc0 = plan_create_internal(&q->sub[0], device, n1, q->split, NW_MODE_BOUNDARY, 0, 1, tuning, false, sc);
-        if (rc0 == NW_OK) rc0 = plan_create_internal(&q->sub[1], device, n1, n2 - q->split, NW_MODE_BOUNDARY, 0, 1, tuning, false, sc);
-        if (rc0 == NW_OK && cudaEventCreateWithFlags(&q->join_ev, cudaEventDisableTiming) != cudaSuccess)
-            rc0 = fail(NW_ERR_CUDA, "cudaEventCreate failed");
-        if (rc0 == NW_OK && dev_alloc(device, q->sub[0]->stream, &q->d_score, 64) != cudaSuccess)
-            rc0 = fail(NW_ERR_CUDA, "device allocation failed");
+        // provisional (four-letter alphabet assumed, like every plan before its first upload): the staircase
+        {
+            bool four[256] = {false};
+            four[1] = four[2] = four[3] = four[4] = true;
+            rc0 = score_build(q, score_can_stair(q, four));
+        }
+        if (rc0 == NW_OK) {
+            cudaSetDevice(dev2);
+            if (cudaEventCreateWithFlags(&q->join_ev, cudaEventDisableTiming) != cudaSuccess) rc0 = fail(NW_ERR_CUDA, "cudaEventCreate failed");
+            cudaSetDevice(device);
+        }
+        if (rc0 == NW_OK && cudaMalloc(&q->d_score, 64) != cudaSuccess) rc0 = fail(NW_ERR_CUDA, "device allocation failed");
         if (rc0 != NW_OK) {
             char keep[512];
             memcpy(keep, g_err, sizeof keep);
@@ -715,8 +761,6 @@ static int plan_create_internal(nw_plan** out, int device, int32_t n1, int32_t n
             memcpy(g_err, keep, sizeof keep);
             return rc0;
         }
-        q->R = q->sub[1]->R; q->warps = q->sub[1]->warps; q->nstrips = q->sub[0]->nstrips + q->sub[1]->nstrips;
-        q->ctas = q->sub[0]->ctas + q->sub[1]->ctas;
         *out = q;
         return NW_OK;
     }
@@ -737,6 +781,7 @@ static int plan_create_internal(nw_plan** out, int device, int32_t n1, int32_t n
     p->sc_match = sc.match; p->sc_mis = sc.mismatch; p->sc_gap = sc.gap; p->local = sc.local != 0;
     p->want_streamed = want_streamed;
     p->mailbox_pooled = same_device_pipeline;
+    p->stair_half = stair_half;
     partition(n1, nparts, part, &p->jstart, &p->ncols);
     rc = plan_alloc(p, tuning);
     if (rc == NW_OK) rc = plan_pick_kernel(p);        // provisional (assumes the four-letter alphabet) so that
@@ -745,6 +790,95 @@ static int plan_create_internal(nw_plan** out, int device, int32_t n1, int32_t n
         return rc;
     }
     *out = p;
+    return NW_OK;
+}
+
+// (Re)build the two sub-plans of a score-mode plan: halves of the table above / below row n2/2 (horizontal cut), or two
+// plans over all rows whose strips share the columns along a staircase.
+static int score_build(nw_plan* q, bool stair)
+{
+    for (int k = 0; k < 2; ++k) {
+        if (q->sub[k]) nw_plan_destroy(q->sub[k]);
+        q->sub[k] = nullptr;
+    }
+    nw_tuning tune;
+    memset(&tune, 0, sizeof tune);
+    tune.rows_per_lane = q->R_req; tune.warps_per_cta = q->warps_req; tune.ctas = q->ctas_req;
+    const Scoring sc = q->scoring_of();
+    int rc;
+    if (stair) {
+        rc = plan_create_internal(&q->sub[0], q->device, q->n1, q->n2, NW_MODE_BOUNDARY, 0, 1, &tune, false, sc, false, 1);
+        if (rc == NW_OK) {
+            tune.rows_per_lane = q->sub[0]->R_req = q->sub[0]->R;       // both halves: the same strip boundaries
+            rc = plan_create_internal(&q->sub[1], q->dev2, q->n1, q->n2, NW_MODE_BOUNDARY, 0, 1, &tune, false, sc, false, 2);
+        }
+    } else {
+        rc = plan_create_internal(&q->sub[0], q->device, q->n1, q->split, NW_MODE_BOUNDARY, 0, 1, &tune, false, sc);
+        if (rc == NW_OK) rc = plan_create_internal(&q->sub[1], q->dev2, q->n1, q->n2 - q->split, NW_MODE_BOUNDARY, 0, 1, &tune, false, sc);
+    }
+    cudaSetDevice(q->device);
+    if (rc != NW_OK) return rc;
+    q->stair = stair;
+    q->uploaded = false;
+    q->R = q->sub[1]->R; q->warps = q->sub[1]->warps; q->nstrips = q->sub[0]->nstrips + q->sub[1]->nstrips;
+    q->ctas = q->sub[0]->ctas + q->sub[1]->ctas;
+    return NW_OK;
+}
+
+// Both halves of a staircase span all rows, i.e. twice as many strips are alive as with the horizontal cut.  On one GPU
+// that pays only while every strip still has a scheduler to itself (measured on the 64gb pair: 2 x 498 strips on 592
+// schedulers, 4.97 ms against 3.84 ms); on two GPUs each half has its own.
+static bool stair_fits(const nw_plan* q)
+{
+    if (q->dev2 != q->device || env_int("NW_CUDA_FORCE_STAIR", 0)) return true;
+    const int sms = g_dev[q->device].sm_count;
+    int R = q->R_req ? q->R_req : env_int("NW_CUDA_R", 0);
+    if (R == 0) R = choose_rows_per_lane_packed(q->n2, q->n1, sms);
+    const long long S = ((long long)q->n2 + 32LL * R - 1) / (32LL * R);
+    return 2 * S <= 4LL * sms;
+}
+
+// the staircase needs the lag-2 kernel on both halves: four letters, small weights, nothing forced through the environment
+static bool score_can_stair(const nw_plan* q, const bool seen[256])
+{
+    uint8_t code[256];
+    return build_code(seen, code) && !env_int("NW_CUDA_NO_STAIR", 0) && !env_int("NW_CUDA_GENERIC", 0) &&
+           !env_int("NW_CUDA_NO_PACKED", 0) && env_int("NW_CUDA_LAG2", 1) != 0 && env_int("NW_CUDA_WS", 0) == 0 &&
+           q->w_max() <= 16 && q->R_req != 1 && env_int("NW_CUDA_R", 0) != 1 && q->n1 > 0 && q->n2 > 0 && stair_fits(q);
+}
+
+// widths of the forward strips (x_0 = n1, then n1 * (S - s) / S) and of the reversed ones (the rest), their tail words
+static int score_set_widths(nw_plan* q)
+{
+    nw_plan *a = q->sub[0], *b = q->sub[1];
+    const int S = a->nstrips;
+    if (!a->lag2 || !b->lag2 || a->ws || b->ws || b->nstrips != S || a->R != b->R || b->pad_top != 0)
+        return fail(NW_ERR_STATE, "staircase score mode: the halves disagree (lag2 %d/%d, strips %d/%d, R %d/%d)", (int)a->lag2,
+                    (int)b->lag2, S, b->nstrips, a->R, b->R);
+    std::vector<int> x((size_t)S), y((size_t)S);
+    for (int s = 0; s < S; ++s) x[s] = (s == 0) ? q->n1 : (int)((long long)q->n1 * (S - s) / S);
+    for (int t = 0; t < S; ++t) y[t] = q->n1 - x[S - 1 - t];
+    nw_plan* h[2] = {a, b};
+    const std::vector<int>* w[2] = {&x, &y};
+    for (int k = 0; k < 2; ++k) {
+        nw_plan* p = h[k];
+        CK(cudaSetDevice(p->device));
+        if ((size_t)S > p->widths_n) {
+            if (p->d_widths) CK(cudaFreeAsync(p->d_widths, p->stream));
+            if (p->d_tails) CK(cudaFreeAsync(p->d_tails, p->stream));
+            p->d_widths = nullptr; p->d_tails = nullptr;
+            CK(dev_alloc(p->device, p->stream, &p->d_widths, sizeof(int) * (size_t)S));
+            CK(dev_alloc(p->device, p->stream, &p->d_tails, sizeof(uint32_t) * 64 * (size_t)S));
+            p->widths_n = (size_t)S;
+        }
+        CK(cudaMemcpyAsync(p->d_widths, w[k]->data(), sizeof(int) * (size_t)S, cudaMemcpyHostToDevice, p->stream));
+        CK(cudaStreamSynchronize(p->stream));       // (the vector is a local)
+        nw::EncodeParams e;
+        memcpy(e.code, p->code, 256);
+        nw::nw_encode_tails_kernel<<<32, 256, 0, p->stream>>>(p->d_s1, p->d_widths, p->d_tails, S, p->ncols, e);
+        CK(cudaGetLastError());
+    }
+    CK(cudaSetDevice(q->device));
     return NW_OK;
 }
 
@@ -769,6 +903,7 @@ static int plan_encode(nw_plan* p, const bool seen[256])
     e.lag2 = p->lag2 ? 1 : 0;
     e.w_match = p->w_match();
     e.w_mis = p->w_mis();
+    memcpy(p->code, e.code, 256);
     nw::nw_encode_kernel<<<64, 256, 0, p->stream>>>(e);
     CK(cudaGetLastError());
     p->uploaded = true;
@@ -781,31 +916,40 @@ extern "C" int nw_plan_upload(nw_plan* p, const int8_t* s1, const int8_t* s2)
     if (p->mode == NW_MODE_SCORE && p->swapped) std::swap(s1, s2);
     if ((p->n1 > 0 && !s1) || (p->n2 > 0 && !s2)) return fail(NW_ERR_ARG, "sequence pointer is NULL");
     if (p->mode == NW_MODE_SCORE) {
-        // top half: s1 against s2[0, split), forwards; bottom half: s1 against s2[split, n2), backwards = forwards on both
-        // sequences reversed.  The reversal happens on the device (the host copy loop used to cost ~0.4 ms per call).
-        nw_plan *a = p->sub[0], *b = p->sub[1];
-        const int nb = p->n2 - p->split;
+        // first half forwards; second half backwards = forwards on both sequences reversed (reversal on the device: the host
+        // copy loop used to cost ~0.4 ms per call).  Horizontal cut: s2[0, split) / s2[split, n2).  Staircase: all of s2 each.
         bool seen[256] = {false};
         const uint8_t* u1 = (const uint8_t*)s1;
         const uint8_t* u2 = (const uint8_t*)s2;
         for (int i = 0; i < p->n1; ++i) seen[u1[i]] = true;
         for (int i = 0; i < p->n2; ++i) seen[u2[i]] = true;
         CK(cudaSetDevice(p->device));
+        int rc = NW_OK;
+        if (score_can_stair(p, seen) != p->stair) {       // (another alphabet than assumed, or a knob changed: rebuild)
+            rc = score_build(p, !p->stair);
+            if (rc) return rc;
+        }
+        nw_plan *a = p->sub[0], *b = p->sub[1];
+        const int na = p->stair ? p->n2 : p->split;       // rows of the first half
+        const int nb = p->stair ? p->n2 : p->n2 - p->split, ob = p->stair ? 0 : p->split;
         if (p->n1 > 0) CK(cudaMemcpyAsync(a->d_s1, u1, (size_t)p->n1, cudaMemcpyHostToDevice, a->stream));
-        if (p->split > 0) CK(cudaMemcpyAsync(a->d_s2, u2, (size_t)p->split, cudaMemcpyHostToDevice, a->stream));
-        int rc = plan_encode(a, seen);
+        if (na > 0) CK(cudaMemcpyAsync(a->d_s2, u2, (size_t)na, cudaMemcpyHostToDevice, a->stream));
+        rc = plan_encode(a, seen);
         if (rc) return rc;
+        CK(cudaSetDevice(b->device));
         if (!b->d_rev) CK(dev_alloc(b->device, b->stream, &b->d_rev, (size_t)p->n1 + (size_t)nb + 1));
         if (p->n1 > 0) {
             CK(cudaMemcpyAsync(b->d_rev, u1, (size_t)p->n1, cudaMemcpyHostToDevice, b->stream));
             nw::nw_reverse_kernel<<<64, 256, 0, b->stream>>>(b->d_rev, b->d_s1, p->n1);
         }
         if (nb > 0) {
-            CK(cudaMemcpyAsync(b->d_rev + p->n1, u2 + p->split, (size_t)nb, cudaMemcpyHostToDevice, b->stream));
+            CK(cudaMemcpyAsync(b->d_rev + p->n1, u2 + ob, (size_t)nb, cudaMemcpyHostToDevice, b->stream));
             nw::nw_reverse_kernel<<<64, 256, 0, b->stream>>>(b->d_rev + p->n1, b->d_s2, nb);
         }
         CK(cudaGetLastError());
         rc = plan_encode(b, seen);
+        if (rc == NW_OK && p->stair) rc = score_set_widths(p);
+        cudaSetDevice(p->device);
         p->uploaded = rc == NW_OK;
         return rc;
     }
@@ -945,6 +1089,8 @@ static int plan_enqueue(nw_plan* p)
         sp.w_match = p->local ? p->sc_match : p->w_match();      // (the local kernel works in H form with the plain scores)
         sp.w_mis = p->local ? p->sc_mis : p->w_mis();
         sp.local_best = p->d_local_best;
+        sp.widths = p->stair_half ? p->d_widths : nullptr;
+        sp.tails = p->stair_half ? p->d_tails : nullptr;
         sp.gap = p->sc_gap;
         sp.margin = 2 * p->w_max() + 10;
         {   // bounded waits (NW_CUDA_SPIN_TIMEOUT_MS, default 20 s; 0 = wait for ever)
@@ -991,11 +1137,27 @@ static int score_enqueue(nw_plan* p)
     int rc = plan_enqueue(b);
     if (rc == NW_OK) rc = plan_enqueue(a);
     if (rc) return rc;
+    CK(cudaSetDevice(b->device));
     CK(cudaEventRecord(p->join_ev, b->stream));
+    CK(cudaSetDevice(a->device));
     CK(cudaStreamWaitEvent(a->stream, p->join_ev, 0));
-    nw::nw_set_int_kernel<<<1, 1, 0, a->stream>>>(p->d_score, INT_MIN);
-    nw::nw_bidir_combine_kernel<<<std::max(1, std::min(148, (p->n1 + 256) / 256)), 256, 0, a->stream>>>(a->d_last_row, b->d_last_row,
-                                                                                                  p->n1, p->d_score);
+    if (p->stair) {
+        nw::StairParams sp;
+        sp.brow_f = a->brow(); sp.pitch_f = a->pitch;
+        sp.brow_b = b->brow(); sp.pitch_b = b->pitch;
+        sp.rcol_f = a->rcol_target + (long long)(a->epoch & 1) * a->mpitch;
+        sp.rcol_b = b->rcol_target + (long long)(b->epoch & 1) * b->mpitch;
+        sp.widths = a->d_widths;
+        sp.nstrips = a->nstrips; sp.strip_rows = 32 * a->R; sp.pad_top = a->pad_top;
+        sp.n1 = p->n1; sp.n2 = p->n2; sp.gap = p->sc_gap;
+        sp.score = p->d_score;
+        nw::nw_set_int_kernel<<<1, 1, 0, a->stream>>>(p->d_score, p->sc_gap * (p->n1 + p->n2));      // the all-gap path
+        nw::nw_stair_combine_kernel<<<std::max(1, std::min(148, a->nstrips)), 256, 0, a->stream>>>(sp);
+    } else {
+        nw::nw_set_int_kernel<<<1, 1, 0, a->stream>>>(p->d_score, INT_MIN);
+        nw::nw_bidir_combine_kernel<<<std::max(1, std::min(148, (p->n1 + 256) / 256)), 256, 0, a->stream>>>(a->d_last_row, b->d_last_row,
+                                                                                                      p->n1, p->d_score);
+    }
     CK(cudaGetLastError());
     p->epoch += 1;
     return NW_OK;
@@ -1008,7 +1170,9 @@ extern "C" int nw_plan_run(nw_plan* p)
     if (p->mode == NW_MODE_SCORE) {
         // the bottom half's stream must not start before the timing event of the top half's stream
         CK(cudaEventRecord(p->sub[0]->ev0, p->sub[0]->stream));
+        CK(cudaSetDevice(p->sub[1]->device));
         CK(cudaStreamWaitEvent(p->sub[1]->stream, p->sub[0]->ev0, 0));
+        CK(cudaSetDevice(p->device));
         int rc = score_enqueue(p);
         if (rc) return rc;
         CK(cudaEventRecord(p->sub[0]->ev1, p->sub[0]->stream));
@@ -1041,7 +1205,9 @@ extern "C" int nw_plan_sync(nw_plan* p)
     if (p->mode == NW_MODE_SCORE) {
         CK(cudaStreamSynchronize(p->sub[1]->stream));
         CK(cudaStreamSynchronize(p->sub[0]->stream));
-        return check_abort(p->device);
+        const int rc2 = (p->dev2 != p->device) ? check_abort(p->dev2) : NW_OK;
+        const int rc1 = check_abort(p->device);
+        return rc1 ? rc1 : rc2;
     }
     CK(cudaStreamSynchronize(p->stream));
     return check_abort(p->device);
@@ -1057,7 +1223,9 @@ extern "C" int nw_plan_time(nw_plan* p, int iters, float* ms_per_fill)
         CK(cudaStreamSynchronize(a->stream));
         CK(cudaStreamSynchronize(b->stream));
         CK(cudaEventRecord(a->ev2, a->stream));
+        CK(cudaSetDevice(b->device));
         CK(cudaStreamWaitEvent(b->stream, a->ev2, 0));
+        CK(cudaSetDevice(a->device));
         for (int i = 0; i < iters; ++i) {
             int rc = score_enqueue(p);        // every combine joins the two streams on a's
             if (rc) return rc;
@@ -1090,7 +1258,9 @@ extern "C" int nw_plan_timer_start(nw_plan* p)
     CK(cudaSetDevice(p->device));
     if (p->mode == NW_MODE_SCORE) {
         CK(cudaEventRecord(p->sub[0]->ev2, p->sub[0]->stream));
+        CK(cudaSetDevice(p->sub[1]->device));
         CK(cudaStreamWaitEvent(p->sub[1]->stream, p->sub[0]->ev2, 0));
+        CK(cudaSetDevice(p->device));
         return NW_OK;
     }
     CK(cudaEventRecord(p->ev2, p->stream));
@@ -1700,6 +1870,7 @@ static std::vector<const void*> all_kernels()
     std::vector<const void*> v;
     for (int regs : {1, 2, 4, 8}) {
         v.push_back((const void*)strip16l2_kernel(regs));
+        v.push_back((const void*)strip16l2_kernel(regs, true));
         v.push_back((const void*)strip16ws_kernel(regs));
         v.push_back((const void*)strip16_kernel(regs));
         v.push_back((const void*)full16_kernel(regs));
@@ -1722,6 +1893,8 @@ static std::vector<const void*> all_kernels()
     v.push_back((const void*)nw::nw_strip_row_kernel);
     v.push_back((const void*)nw::nw_set_int_kernel);
     v.push_back((const void*)nw::nw_bidir_combine_kernel);
+    v.push_back((const void*)nw::nw_stair_combine_kernel);
+    v.push_back((const void*)nw::nw_encode_tails_kernel);
     v.push_back((const void*)nw::nw_reverse_kernel);
     v.push_back((const void*)nw::nw_traceback_kernel);
     v.push_back((const void*)nw::nw_tile_trace_kernel);
@@ -1905,24 +2078,25 @@ static int run_pipeline(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t 
 
 // score only, through a cached NW_MODE_SCORE plan (what the reference driver reads in boundary mode: driver.cpp:35)
 static int run_score_oneshot(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int32_t* score,
-                             const Scoring& sc = Scoring())
+                             const Scoring& sc = Scoring(), int gpus = 1)
 {
     Trace tr;
     static std::mutex mu;
     static nw_plan* cached = nullptr;
-    static int c_n1 = -1, c_n2 = -1;         // the caller's sizes (a score plan may hold them swapped)
+    static int c_n1 = -1, c_n2 = -1, c_gpus = -1;         // the caller's sizes (a score plan may hold them swapped)
     static Scoring c_sc;
     std::lock_guard<std::mutex> lk(mu);
     int rc = NW_OK;
-    if (!cached || c_n1 != n1 || c_n2 != n2 || !(c_sc == sc)) {
+    if (!cached || c_n1 != n1 || c_n2 != n2 || c_gpus != gpus || !(c_sc == sc)) {
         if (cached) nw_plan_destroy(cached);
         cached = nullptr;
         c_n1 = c_n2 = -1;
-        rc = plan_create_internal(&cached, 0, n1, n2, NW_MODE_SCORE, 0, 1, nullptr, false, sc);
+        rc = plan_create_internal(&cached, 0, n1, n2, NW_MODE_SCORE, 0, gpus, nullptr, false, sc);
         if (rc) return rc;
         c_n1 = n1;
         c_n2 = n2;
         c_sc = sc;
+        c_gpus = gpus;
     }
     tr.mark("plan_create");
     rc = nw_plan_upload(cached, s1, s2);
@@ -1947,8 +2121,12 @@ static int fill_scored(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n
     if (mode == NW_MODE_FULL) return run_pipeline(s1, n1, s2, n2, mode, ngpus, table, nullptr, nullptr, nullptr, sc);
     if (mode != NW_MODE_BOUNDARY) return fail(NW_ERR_ARG, "unknown mode %d", mode);
     int32_t score = 0;
-    int rc = (ngpus == 1 && !sc.local && !env_int("NW_CUDA_NO_BIDIR", 0))
-                 ? run_score_oneshot(s1, n1, s2, n2, &score, sc)
+    // one GPU: score mode (two half-length chains); more: score mode with one half on each of the first two GPUs (along a
+    // staircase their chains are shorter still, and there is nothing a third GPU could shorten: a single fill is bound by
+    // its critical path).  NW_CUDA_NO_BIDIR=1: one forward fill, column strips over all GPUs.
+    if (ngpus < 1) return fail(NW_ERR_ARG, "ngpus must be >= 1");
+    int rc = (!sc.local && !env_int("NW_CUDA_NO_BIDIR", 0))
+                 ? run_score_oneshot(s1, n1, s2, n2, &score, sc, std::min(ngpus, 2))
                  : run_pipeline(s1, n1, s2, n2, mode, ngpus, nullptr, nullptr, nullptr, &score, sc);
     if (rc == NW_OK) table[((long long)n1 + 1) * ((long long)n2 + 1) - 1] = score;     // what driver.cpp:35 reads
     return rc;

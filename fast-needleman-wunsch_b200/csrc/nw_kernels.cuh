@@ -104,6 +104,11 @@ struct StripParams {
     unsigned long long spin_ns;  // not hang us.  Waiting warps re-read only the DEVICE word (a host read costs microseconds).
     int w_match, w_mis;          // G-form weights: max(M - 2g, 0), max(X - 2g, 0)  (default scoring: 3, 2)
     int gap;                     // g (default -1): H = G + g*(i + j) where cells leave a kernel
+    // score mode along a staircase (lag-2 kernel only): strip s sweeps only its first widths[s] columns (a multiple of 32, or
+    // ncols) and is frozen beyond them, like every strip is beyond the table's last column; tails[s * 64 + k] is the selector
+    // word of column widths[s] + k with the low half (column >= width) made virtual
+    const int* widths;
+    const uint32_t* tails;
     int4* local_best;            // local alignment (nw_local.cuh): per strip {best score, row, column, 0}
     int margin;                  // packed kernels: slack below the warp's minimum when re-basing (2 * max weight + 10)
     unsigned long long* times;   // nstrips x 4: %globaltimer (ns) when a strip has its first top-row block and when it
@@ -397,8 +402,9 @@ __global__ void nw_encode_kernel(const EncodeParams e)
         for (int x = tid; x < e.nrows_padded / 2; x += nth) {
             const int s = x / (32 * R), rem = x - s * 32 * R, L = rem / R, r = rem - L * R;
             const int klo = s * 64 * R + L * R + r - e.pad_top, khi = klo + 32 * R;
-            e.rsel[2 * x] = (klo >= 0) ? weight_word(e.code[e.s2[klo]], e.w_match, e.w_mis) : 0u;
-            e.rsel[2 * x + 1] = (khi >= 0) ? weight_word(e.code[e.s2[khi]], e.w_match, e.w_mis) : 0u;
+            // (rows past n2 exist when the padding sits at the bottom: pad_top == 0 on the reversed half of a staircase)
+            e.rsel[2 * x] = (klo >= 0 && klo < e.n2) ? weight_word(e.code[e.s2[klo]], e.w_match, e.w_mis) : 0u;
+            e.rsel[2 * x + 1] = (khi >= 0 && khi < e.n2) ? weight_word(e.code[e.s2[khi]], e.w_match, e.w_mis) : 0u;
         }
         return;
     }
@@ -422,6 +428,19 @@ __global__ void nw_encode_kernel(const EncodeParams e)
         if (k >= 0) v = e.generic ? (uint32_t)e.s2[k] : (0x5550u | e.code[e.s2[k]]);
         else v = e.generic ? 0x200u : 0xCCCCu;
         e.rsel[q] = v;
+    }
+}
+
+// staircase score mode: selector words of the 64 columns behind every strip's own width (low half virtual, high half real)
+__global__ void nw_encode_tails_kernel(const uint8_t* __restrict__ s1, const int* __restrict__ widths, uint32_t* tails,
+                                       int nstrips, int ncols, const EncodeParams e)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int x = tid; x < nstrips * 64; x += nth) {
+        const int s = x >> 6, k = x & 63;
+        const int c2 = widths[s] + k - 64;      // the high half's column: inside the strip's width whenever it is >= 0
+        const uint32_t n2 = (c2 >= 0 && c2 < ncols) ? 4u + e.code[s1[c2]] : 0xCu;
+        tails[x] = 0x8u | 0x80u | (n2 << 8) | 0xC000u;
     }
 }
 
@@ -493,6 +512,44 @@ __global__ void __launch_bounds__(256) nw_bidir_combine_kernel(const int32_t* __
         int v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : INT_MIN;
         v = __reduce_max_sync(FULL_MASK, v);
         if (threadIdx.x == 0 && v != INT_MIN) atomicMax(score, v);
+    }
+}
+
+// NW_MODE_SCORE along a staircase: the forward plan filled, of strip s (table rows (r_s, r_s+1]), columns [0, x_s]; the
+// reversed plan filled the rest.  Every monotone path crosses the 4-connected staircase
+//   { (r_s+1, j) : x_s+1 <= j <= x_s }  and  { (i, x_s) : r_s < i < r_s+1 },   s = 0 .. S-1,  x_S = 0,
+// in a vertex, so H[n2][n1] = max over those vertices of F + B.  F comes from the forward strips' bottom rows and right
+// columns, B from the reversed plan's (strip t = S-1-s covers the same table rows; its predecessor's bottom row is table
+// row r_s+1).  All values are in G form: F_H + B_H = F_G + B_G + gap * (n1 + n2).
+struct StairParams {
+    const int2* brow_f;   long long pitch_f;
+    const int2* brow_b;   long long pitch_b;
+    const int2* rcol_f;   // indexed by table row
+    const int2* rcol_b;   // indexed by reversed table row
+    const int* widths;    // x_s
+    int nstrips, strip_rows, pad_top, n1, n2, gap;
+    int32_t* score;       // preset to gap * (n1 + n2): the all-gap path through the corner
+};
+__global__ void __launch_bounds__(256) nw_stair_combine_kernel(const StairParams p)
+{
+    __shared__ int red[8];
+    int best = 0;
+    for (int s = blockIdx.x; s < p.nstrips; s += gridDim.x) {
+        const int xs = p.widths[s], xn = (s + 1 < p.nstrips) ? p.widths[s + 1] : 0;
+        const int r_lo = max(s * p.strip_rows - p.pad_top, 0), r_hi = (s + 1) * p.strip_rows - p.pad_top;
+        const int t = p.nstrips - 1 - s;
+        const int2* bf = p.brow_f + (long long)s * p.pitch_f;
+        const int2* bb = (t >= 1) ? p.brow_b + (long long)(t - 1) * p.pitch_b : nullptr;
+        for (int j = xn + threadIdx.x; j <= xs; j += blockDim.x) best = max(best, bf[j].y + (bb ? bb[p.n1 - j].y : 0));
+        for (int i = r_lo + 1 + threadIdx.x; i < r_hi; i += blockDim.x) best = max(best, p.rcol_f[i].y + p.rcol_b[p.n2 - i].y);
+    }
+    best = __reduce_max_sync(FULL_MASK, best);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0;
+        v = __reduce_max_sync(FULL_MASK, v);
+        if (threadIdx.x == 0) atomicMax(p.score, v + p.gap * (p.n1 + p.n2));
     }
 }
 

@@ -46,6 +46,13 @@ __device__ __forceinline__ void cp_async8(uint32_t* smem_dst, const uint32_t* gs
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async4_if(bool pred, uint32_t* smem_dst, const uint32_t* gsrc)      // predicated, no branch
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p cp.async.ca.shared.global [%0], [%1], 4; }" ::"r"(d), "l"(gsrc),
+                 "r"((int)pred)
+                 : "memory");
+}
 __device__ __forceinline__ void cp_async8_if(bool pred, uint32_t* smem_dst, const uint32_t* gsrc)      // predicated, no branch
 {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -125,7 +132,9 @@ __device__ __forceinline__ void sweep16l2(uint32_t (&h)[R], uint32_t& dprev, con
     }
 }
 
-template <int R>
+// STAIR: score mode along a staircase -- the strip has its own width (StripParams::widths); instantiated separately so
+// that the plain kernel's code is exactly what it was.
+template <int R, bool STAIR>
 __device__ __forceinline__ void run_strip16l2(const StripParams& p, const int s, const int lane, uint32_t* smem)
 {
     constexpr int SH = 64 * R;
@@ -134,7 +143,12 @@ __device__ __forceinline__ void run_strip16l2(const StripParams& p, const int s,
     uint32_t* sout = sin + 64;                         // 2 x 32, by block parity
     int2* stag = reinterpret_cast<int2*>(sout + 64);   // 2 x 32 tagged words of the top boundary row, by block parity
     const uint32_t* ringm = ring + (lane & 1) * L2_COPY_WORDS;
-    const int ncols = p.ncols;
+    // staircase score mode: this strip's own width.  Beyond it the strip is frozen exactly like every strip is beyond the
+    // table's last column -- its selector words are virtual (weight 0) from there on
+    const int ncols = STAIR ? p.widths[s] : p.ncols;
+    const int xcut = (ncols < p.ncols) ? ncols : 0x7fffff00;
+    const uint32_t* const tail = STAIR ? p.tails + s * 64 : nullptr;
+    const uint32_t* const virt = p.wq + p.ncols + 64;                  // an all-virtual word (the right padding of wq)
     const int q_lo = s * SH + lane * R;               // first padded row of the low half; the high half is 32*R below
     const int i_lo = q_lo - p.pad_top;                // table row just above the low half's first row (may be <= 0)
     const int i_hi = i_lo + 32 * R;
@@ -160,8 +174,18 @@ __device__ __forceinline__ void run_strip16l2(const StripParams& p, const int s,
     const int fskew = (lane >> 4) * 2;
     auto fill = [&](int c0) {      // columns [c0, c0 + 32); the array is zero-padded on both sides
         const int w = (c0 + fx + fskew) & 255;
-        cp_async8(fdst + w, wq + c0 + fx);
-        cp_async8_if(w < L2_MIRROR, fdst + 256 + w, wq + c0 + fx);
+        if (STAIR) {       // word by word: the cut may fall between the two (selects, no branch)
+            const int ca = c0 + fx, cb2 = ca + 1;
+            const uint32_t* sa = (ca >= xcut) ? ((ca < xcut + 64) ? tail + (ca - xcut) : virt) : wq + ca;
+            const uint32_t* sb = (cb2 >= xcut) ? ((cb2 < xcut + 64) ? tail + (cb2 - xcut) : virt) : wq + cb2;
+            cp_async4_if(true, fdst + w, sa);
+            cp_async4_if(true, fdst + w + 1, sb);
+            cp_async4_if(w < L2_MIRROR, fdst + 256 + w, sa);
+            cp_async4_if(w < L2_MIRROR, fdst + 256 + w + 1, sb);
+        } else {
+            cp_async8(fdst + w, wq + c0 + fx);
+            cp_async8_if(w < L2_MIRROR, fdst + 256 + w, wq + c0 + fx);
+        }
         cp_async_commit();
     };
     fill(0);
@@ -324,19 +348,20 @@ __device__ __forceinline__ void run_strip16l2(const StripParams& p, const int s,
         for (int r = 0; r < R; ++r) {
             const int a = i_lo + 1 + r, b = i_hi + 1 + r;
             const int va = (int)(short)(h[r] & 0xffffu) + base, vb = ((int)h[r] >> 16) + base;
+            // (a, b <= n2: rows below the table exist when the padding sits at the bottom)
             if (p.rcol_sys) {
-                if (a >= 1) st_tagged_sys(p.rcol + a, p.epoch, va);
-                if (b >= 1) st_tagged_sys(p.rcol + b, p.epoch, vb);
+                if (a >= 1 && (!STAIR || a <= p.n2)) st_tagged_sys(p.rcol + a, p.epoch, va);
+                if (b >= 1 && (!STAIR || b <= p.n2)) st_tagged_sys(p.rcol + b, p.epoch, vb);
             } else {
-                if (a >= 1) st_tagged_gpu(p.rcol + a, p.epoch, va);
-                if (b >= 1) st_tagged_gpu(p.rcol + b, p.epoch, vb);
+                if (a >= 1 && (!STAIR || a <= p.n2)) st_tagged_gpu(p.rcol + a, p.epoch, va);
+                if (b >= 1 && (!STAIR || b <= p.n2)) st_tagged_gpu(p.rcol + b, p.epoch, vb);
             }
         }
     }
     __syncwarp();
 }
 
-template <int R>
+template <int R, bool STAIR = false>
 __global__ void __launch_bounds__(512) nw_strip16l2_kernel(const StripParams p)
 {
     extern __shared__ __align__(16) uint32_t nw_smem[];
@@ -344,7 +369,7 @@ __global__ void __launch_bounds__(512) nw_strip16l2_kernel(const StripParams p)
     uint32_t* smem = nw_smem + warp * L2_SMEM_WORDS_PER_WARP;
     const int slot = blockIdx.x * nwarps + warp, nslots = gridDim.x * nwarps;
     wait_mailbox_free(p);
-    for (int s = slot; s < p.nstrips; s += nslots) run_strip16l2<R>(p, s, lane, smem);
+    for (int s = slot; s < p.nstrips; s += nslots) run_strip16l2<R, STAIR>(p, s, lane, smem);
 }
 
 }  // namespace nw

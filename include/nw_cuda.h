@@ -37,10 +37,13 @@ extern "C" {
 /* memory modes (BASELINE.json configs[2]) */
 #define NW_MODE_BOUNDARY 0    /* keep strip boundary rows + right column only; host gets the score        */
 #define NW_MODE_FULL 1        /* materialise every cell, as the reference does (src/serial/serial.cpp:31)    */
-#define NW_MODE_SCORE 2       /* score only, meeting in the middle: the top half of the table is filled forwards and,
-                                 concurrently, the bottom half backwards (= forwards on the reversed sequences);
-                                 H[n2][n1] = max_j F[m][j] + B[m][j].  Two dependency chains of half the length
-                                 instead of one; only nw_plan_score is available on such a plan                 */
+#define NW_MODE_SCORE 2       /* score only, meeting in the middle: one half of the table is filled forwards and,
+                                 concurrently, the other backwards (= forwards on the reversed sequences); the score
+                                 is the maximum of F + B over a cut that every path crosses -- the row n2/2, or, when
+                                 every strip of both halves can have a scheduler to itself (small tables, or two GPUs),
+                                 a staircase from the top right to the bottom left corner, which also takes the strips'
+                                 start-up lag off the critical path.  Same number of cell updates, bit-exact score;
+                                 only nw_plan_score / nw_plan_best are available on such a plan                   */
 
 /* ------------------------------------------------------------------------------------------------------------
  * Library / device
@@ -63,7 +66,8 @@ int nw_cuda_device_info(int device, char* name, int name_len, int* sm_count, int
  * Mode and GPU count come from the environment (the driver's argv is fixed, src/common/driver.cpp:2):
  *   NW_CUDA_MODE = full (default: every cell written, like the reference) | boundary (only table[size-1], computed
  *                  in NW_MODE_SCORE fashion)
- *   NW_CUDA_GPUS = 1 (default) | 2 | 4 | 8   column strips across devices of this process */
+ *   NW_CUDA_GPUS = 1 (default) | 2 | 4 | 8   devices of this process: column strips (full mode; boundary mode beyond two),
+ *                  one score-mode half per device (boundary mode on two) */
 int nw_cuda_fill(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int32_t* table);
 int nw_cuda_fill_ex(const int8_t* s1, int32_t n1, const int8_t* s2, int32_t n2, int32_t* table,
                     int mode, int ngpus);
@@ -128,7 +132,8 @@ typedef struct nw_tuning {
     int reserved[5];
 } nw_tuning;
 
-/* mode: NW_MODE_BOUNDARY, NW_MODE_FULL or NW_MODE_SCORE (single part only; offers nw_plan_upload / run / sync / time /
+/* mode: NW_MODE_BOUNDARY, NW_MODE_FULL or NW_MODE_SCORE (part 0 of 1: both halves on `device`; part 0 of 2: one half on
+ * `device`, the other on `device + 1`, no traffic between them until the final combine; offers nw_plan_upload / run / sync / time /
  * score).  Kernel choice is automatic: packed s16x2 kernels when at most four distinct byte values occur in the two
  * sequences (always true for bdna), 32-bit kernels otherwise. */
 int nw_plan_create(nw_plan** out, int device, int32_t n1, int32_t n2, int mode,

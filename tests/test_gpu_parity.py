@@ -325,6 +325,65 @@ def test_multi_gpu_64gb_score(gpu):
                 p.close()
 
 
+@pytest.mark.parametrize("shape", [(1, 1), (40, 3), (3, 40), (700, 701), (5000, 2999), (2999, 5000), (20011, 9000)])
+def test_score_mode_two_gpus(gpu, oracle, shape):
+    # NW_MODE_SCORE, part 0 of 2: the forward half on device 0, the reversed half on device 1, cut along a staircase
+    _need_gpus(gpu, 2)
+    n1, n2 = shape
+    s1, s2 = synth_pair(300 + n1 + n2, n1, n2, 5)
+    want = oracle.score(s1, s2)
+    with gpu.Plan(n1, n2, mode=gpu.NW_MODE_SCORE, part=0, nparts=2) as p:
+        p.upload(s1, s2)
+        for _ in range(2):
+            p.run()
+            assert p.score() == want
+        assert p.time(2) > 0 and p.score() == want
+    g1, g2 = synth_pair(5, n1, n2, 90)                    # a generic alphabet: horizontal cut, still one half per GPU
+    with gpu.Plan(n1, n2, mode=gpu.NW_MODE_SCORE, part=0, nparts=2) as p:
+        p.upload(g1, g2)
+        p.run()
+        assert p.score() == oracle.score(g1, g2)
+
+
+@pytest.mark.parametrize("name", ["smid", "2gb", "mid", "big", "64gb"])
+def test_score_mode_two_gpus_fixtures(gpu, name):
+    _need_gpus(gpu, 2)
+    s1, s2 = load_pair(name)
+    with gpu.Plan(s1.size, s2.size, mode=gpu.NW_MODE_SCORE, part=0, nparts=2) as p:
+        p.upload(s1, s2)
+        p.run()
+        assert p.score() == GOLDEN["fixtures"][name]["score"]
+    if name == "smid":
+        t = np.zeros((s2.size + 1) * (s1.size + 1), dtype=np.int32)
+        gpu.needlemanWunsch(s1, s2, t, mode=gpu.NW_MODE_BOUNDARY, ngpus=2)      # the plug-in call on two GPUs
+        assert t[-1] == GOLDEN["fixtures"][name]["score"]
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (33, 31), (700, 701), (5000, 2999), (2999, 5000), (9000, 20011), (20011, 9000)])
+def test_score_mode_staircase_and_horizontal_cut_agree(gpu, oracle, monkeypatch, shape):
+    # one GPU: the staircase is chosen while twice the strips still fit the schedulers; both cuts must give the oracle's score
+    n1, n2 = shape
+    s1, s2 = synth_pair(400 + n1 + n2, n1, n2, 5)
+    want = oracle.score(s1, s2)
+    for no_stair, force in (("0", "1"), ("1", "0"), ("0", "0")):
+        monkeypatch.setenv("NW_CUDA_NO_STAIR", no_stair)
+        monkeypatch.setenv("NW_CUDA_FORCE_STAIR", force)
+        for R in (0, 2, 16):
+            with gpu.Plan(n1, n2, mode=gpu.NW_MODE_SCORE, rows_per_lane=R) as p:
+                p.upload(s1, s2)
+                p.run()
+                assert p.score() == want, (no_stair, force, R)
+
+
+def test_score_mode_forced_staircase_64gb(gpu, monkeypatch):
+    monkeypatch.setenv("NW_CUDA_FORCE_STAIR", "1")
+    s1, s2 = load_pair("64gb")
+    with gpu.Plan(s1.size, s2.size, mode=gpu.NW_MODE_SCORE) as p:
+        p.upload(s1, s2)
+        p.run()
+        assert p.score() == GOLDEN["fixtures"]["64gb"]["score"]
+
+
 # ---- API behaviour ------------------------------------------------------------------------------------------------------
 def test_error_behaviour(gpu):
     s = np.ones(100, dtype=np.int8)
