@@ -523,6 +523,12 @@ def gpu_arm(args):
         if world > 1:
             dist.barrier()
 
+    def cpu_barrier():
+        """A barrier that leaves the GPUs alone (gloo all-reduce of a host tensor): the NCCL barrier is a kernel that spins on
+        every waiting rank's GPU, and rank 0 is about to use those GPUs from its own process."""
+        if world > 1:
+            dist.all_reduce(torch.zeros(1))
+
     def one_step():
         """One fill, alone: launch, wait for it, (N > 1) wait for everybody.  Returns this rank's device ms."""
         plan.run()
@@ -591,6 +597,8 @@ def gpu_arm(args):
     # ---- score-only mode with one half per GPU (N >= 2; rank 0 drives devices 0 and 1 in-process) --------------------------
     if world >= 2 and not full:
         barrier()
+        torch.cuda.synchronize()
+        cpu_barrier()
         if rank == 0:
             nw.init(1)
             with nw.Plan(n1, n2, mode=nw.NW_MODE_SCORE, device=0, part=0, nparts=2) as splan:
@@ -605,7 +613,7 @@ def gpu_arm(args):
                                       "start-up lag overlaps their shorter sweeps); no traffic between the GPUs until the "
                                       "combine kernel reads the second half's boundary rows through peer access",
                               "launches_per_step": splan.launches_per_run()}
-        barrier()
+        cpu_barrier()
 
     # ---- end to end: HOST sequences in, fill, result out, every step -----------------------------------------------------
     table = None
@@ -641,7 +649,7 @@ def gpu_arm(args):
 
         def e2e_step():
             r = plugin_boundary_call(nw, s1, s2, ngpus=world) if rank == 0 else None
-            barrier()
+            cpu_barrier()
             return r
         e2e_path = (f"nw_cuda_fill_ex(host s1, host s2, host table, NW_MODE_BOUNDARY, {world}) per step from rank 0 -- the call "
                     "csrc/cuda.cpp makes with NW_CUDA_GPUS=N: score-only mode with one half of the table on each of the first "
