@@ -1974,6 +1974,20 @@ extern "C" int nw_cuda_init(int device)
             if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
             cudaGetLastError();
         }
+        // score mode with one half per GPU: device 0's combine kernel reads device 1's boundary rows, which live in
+        // device 1's pool -- mapping a pre-faulted pool into a peer costs ~0.4 s, so it happens here, not in the timed call
+        if (rc == NW_OK && device == 1) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, 0, 1));
+            if (can) {
+                cudaMemAccessDesc desc;
+                memset(&desc, 0, sizeof desc);
+                desc.location.type = cudaMemLocationTypeDevice;
+                desc.location.id = 0;
+                desc.flags = cudaMemAccessFlagsProtReadWrite;
+                CK(cudaMemPoolSetAccess(d.pool, &desc, 1));
+            }
+        }
     }
     if (rc == NW_OK) {
         std::lock_guard<std::mutex> lk(g_mu);
