@@ -395,11 +395,14 @@ def time_pair(nw, name, mode, steps, device, cpu_pairs):
     return out
 
 
-TALL = {"n1": 262144, "n2": 1048576, "seed": 20261018, "score": -524289}     # score: oracle/nw_oracle.c on the host (666 s, one core)
+# score: oracle/nw_oracle.c (two-row restatement of serial.cpp) on one host core, 2 678 s.  (The round's first choice,
+# 262 144 x 1 048 576 / seed 20261018 / score -524289, is critical-path-bound again from 4 GPUs on -- 44.9 / 25.1 / 23.7 ms at
+# 1 / 2 / 4 -- because 4096 strips x 200 steps of start-up lag is a floor no column split removes; this one is four times larger.)
+TALL = {"n1": 524288, "n2": 2097152, "seed": 20261019, "score": -1048577}
 
 
 def tall_pair(nw, torch, dist, pipeline, world, rank, device, steps=3):
-    """Secondary measurement at every N: a THROUGHPUT-bound single pair (4096 strips of 256 rows against 592 warp slots per
+    """Secondary measurement at every N: a THROUGHPUT-bound single pair (8192 strips of 256 rows against 592 warp slots per
     GPU, so every scheduler always has a strip to work on), column strips over the N ranks exactly like the headline pair.
     This is the regime in which the mpi-vert decomposition (src/mpi/mpi-vert.cpp:17-105) pays: the headline pair is
     bound by its critical path on one GPU already."""
