@@ -55,6 +55,28 @@ def test_no_cpu_fallback_without_device(nw):
         nw.needlemanWunsch(s, s)
     with pytest.raises(nw.NwCudaError):
         nw.batch_scores(s.reshape(2, 4), s.reshape(2, 4))
+    # the widened entry points: scoring parameters, Smith-Waterman, alignment without a table, plans
+    for call in (lambda: nw.score(s, s, scoring=(2, -1, -2)), lambda: nw.best(s, s, (2, -1, -2, 1)),
+                 lambda: nw.needlemanWunsch(s, s, scoring=(5, -4, -3)), lambda: nw.align(s, s),
+                 lambda: nw.batch_scores(s.reshape(2, 4), s.reshape(2, 4), scoring=(2, -1, -2)),
+                 lambda: nw.Plan(8, 8), lambda: nw.Plan(8, 8, mode=nw.NW_MODE_SCORE, nparts=2),
+                 lambda: nw.Plan(8, 8, scoring=(1, 0, -1, 1)), lambda: nw.dpx_peak(0)):
+        with pytest.raises(nw.NwCudaError):
+            call()
+
+
+def test_scoring_arguments_are_validated_before_any_device_work(nw):
+    # argument errors carry their own code and text, with or without a device
+    s = np.ones(8, dtype=np.int8)
+    for bad in ((1, 0, 1, 1), (1, 0, -1, 7)):
+        with pytest.raises(nw.NwCudaError, match="-2"):
+            nw.best(s, s, bad)
+    sc = nw.Scoring(1, 0, -1, 0)
+    sc.reserved[2] = 5
+    with pytest.raises(nw.NwCudaError, match="reserved"):
+        nw.score(s, s, scoring=sc)
+    with pytest.raises(nw.NwCudaError, match="overflow"):
+        nw.Plan(1 << 20, 1 << 20, scoring=(5000, 0, -1))
 
 
 def test_product_never_touches_the_oracle(nw):
