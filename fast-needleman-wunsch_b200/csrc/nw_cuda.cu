@@ -1747,13 +1747,12 @@ extern "C" int nw_plans_traceback(nw_plan* const* parts, int nparts, int8_t* a1,
 extern "C" int nw_plan_traceback(nw_plan* p, int8_t* a1, int8_t* a2, int32_t* len)
 {
     if (!p || !a1 || !a2 || !len) return fail(NW_ERR_ARG, "bad argument");
-    if (p->mode == NW_MODE_BOUNDARY) {          // from the checkpoint rows: no table
+    if (p->mode == NW_MODE_BOUNDARY && !p->local) {          // from the checkpoint rows: no table
         if (p->nparts != 1) return fail(NW_ERR_ARG, "a pipeline is traced back through nw_plans_traceback (all its parts)");
         nw_plan* one[1] = {p};
         return nw_plans_traceback(one, 1, a1, a2, len);
     }
     if (p->mode != NW_MODE_FULL) return fail(NW_ERR_STATE, "traceback needs a boundary-mode or full-table plan");
-    if (p->local) return fail(NW_ERR_UNSUPPORTED, "traceback of a local alignment is not implemented");
     if (p->nparts != 1 || p->streamed) return fail(NW_ERR_UNSUPPORTED, "table traceback needs the whole table on one device");
     if (p->epoch == 0) return fail(NW_ERR_STATE, "no fill has been run");
     CK(cudaSetDevice(p->device));
@@ -1762,8 +1761,12 @@ extern "C" int nw_plan_traceback(nw_plan* p, int8_t* a1, int8_t* a2, int32_t* le
     int* d_len = nullptr;
     CK(dev_alloc(p->device, p->stream, &d_out, 2 * cap));
     CK(dev_alloc(p->device, p->stream, &d_len, sizeof(int)));
-    nw::nw_traceback_kernel<<<1, 256, 0, p->stream>>>(p->d_table, p->tpitch, p->d_s1, p->d_s2, p->n1, p->n2, d_out,
-                                                      d_out + cap, d_len, p->sc_match, p->sc_mis, p->sc_gap);
+    if (p->local)       // from the best cell back to the first zero
+        nw::nw_traceback_local_kernel<<<1, 256, 0, p->stream>>>(p->d_table, p->tpitch, p->d_s1, p->d_s2, p->d_score, d_out,
+                                                                d_out + cap, d_len, p->sc_match, p->sc_mis, p->sc_gap);
+    else
+        nw::nw_traceback_kernel<<<1, 256, 0, p->stream>>>(p->d_table, p->tpitch, p->d_s1, p->d_s2, p->n1, p->n2, d_out,
+                                                          d_out + cap, d_len, p->sc_match, p->sc_mis, p->sc_gap);
     int rc = (cudaGetLastError() == cudaSuccess) ? NW_OK : fail(NW_ERR_CUDA, "traceback launch failed");
     if (rc == NW_OK) rc = fetch_reversed_path(p->stream, d_out, cap, d_len, a1, a2, len);
     cudaFreeAsync(d_out, p->stream);
@@ -1898,6 +1901,7 @@ static std::vector<const void*> all_kernels()
     v.push_back((const void*)nw::nw_reverse_kernel);
     v.push_back((const void*)nw::nw_traceback_kernel);
     v.push_back((const void*)nw::nw_tile_trace_kernel);
+    v.push_back((const void*)nw::nw_traceback_local_kernel);
     return v;
 }
 

@@ -604,9 +604,11 @@ __global__ void nw_presence_kernel64(const uint8_t* s, long long n, uint32_t* bi
 // segments), thread 0 walks inside it until it leaves, and the window is re-staged.  Rule per cell (the reference
 // defines none; this is the oracle's): diagonal if H[i][j] == H[i-1][j-1] + (s1[j-1]==s2[i-1] ? match : mismatch), else up
 // if H[i][j] == H[i-1][j] + gap, else left.  Output: the two gapped sequences REVERSED (gap = 0, README.md:8).
-// TILE = false: the table is the whole table; walk to (0, 0), moves along row 0 / column 0 are forced.
-// TILE = true:  the table is one tile of it (row 0 / column 0 = its top / left boundary); stop on reaching either.
-// pos[0..2] (shared) = i, j, emitted; s1[j-1] / s2[i-1] are the letters of table column j / row i of THIS table.
+// MODE WALK_TABLE: the table is the whole table; walk to (0, 0), moves along row 0 / column 0 are forced.
+// MODE WALK_TILE:  the table is one tile of it (row 0 / column 0 = its top / left boundary); stop on reaching either.
+// MODE WALK_LOCAL: a Smith-Waterman table; stop at the first cell whose value is 0 (pos[3] is set).
+// pos[0..3] (shared) = i, j, emitted, finished; s1[j-1] / s2[i-1] are the letters of table column j / row i of THIS table.
+constexpr int WALK_TABLE = 0, WALK_TILE = 1, WALK_LOCAL = 2;
 constexpr int TB_W = 64;
 struct WalkSmem {
     int win[TB_W][TB_W + 1];
@@ -619,14 +621,15 @@ struct RowMajorCells {
     static constexpr bool ROW_FASTEST = false;      // staging order that coalesces: columns fastest
     __device__ __forceinline__ int operator()(int i, int j) const { return table[(long long)i * tpitch + j]; }
 };
-template <bool TILE, class Cells>
+template <int MODE, class Cells>
 __device__ __forceinline__ void walk_table(const Cells cells, const uint8_t* __restrict__ s1,
                                            const uint8_t* __restrict__ s2, WalkSmem& w, volatile int* pos, uint8_t* out1,
                                            uint8_t* out2, int sc_match, int sc_mis, int sc_gap)
 {
     for (;;) {
         const int i = pos[0], j = pos[1];
-        if (TILE ? (i == 0 || j == 0) : (i == 0 && j == 0)) break;
+        if (MODE == WALK_TABLE ? (i == 0 && j == 0) : (i == 0 || j == 0)) break;
+        if (MODE == WALK_LOCAL && pos[3] != 0) break;
         const int wi0 = max(i - (TB_W - 1), 0), wj0 = max(j - (TB_W - 1), 0);     // window = rows wi0..i, cols wj0..j
         const int nr = i - wi0 + 1, nc = j - wj0 + 1;
         if (Cells::ROW_FASTEST) {
@@ -651,7 +654,8 @@ __device__ __forceinline__ void walk_table(const Cells cells, const uint8_t* __r
             // walk while the three neighbours are inside the window, or the move is forced by a table edge
             for (;;) {
                 const int gi = wi0 + a, gj = wj0 + b;
-                if (TILE ? (gi == 0 || gj == 0) : (gi == 0 && gj == 0)) break;
+                if (MODE == WALK_TABLE ? (gi == 0 && gj == 0) : (gi == 0 || gj == 0)) break;
+                if (MODE == WALK_LOCAL && w.win[a][b] == 0) { pos[3] = 1; break; }
                 int move;                                      // 0 diag, 1 up, 2 left
                 if (gi == 0) move = 2;
                 else if (gj == 0) move = 1;
@@ -683,10 +687,25 @@ __global__ void __launch_bounds__(256) nw_traceback_kernel(const int32_t* __rest
                                                            int sc_match, int sc_mis, int sc_gap)
 {
     __shared__ WalkSmem w;
-    __shared__ int pos[3];                 // i, j, emitted
-    if (threadIdx.x == 0) { pos[0] = n2; pos[1] = n1; pos[2] = 0; }
+    __shared__ int pos[4];                 // i, j, emitted, finished
+    if (threadIdx.x == 0) { pos[0] = n2; pos[1] = n1; pos[2] = 0; pos[3] = 0; }
     __syncthreads();
-    walk_table<false>(RowMajorCells{table, tpitch}, s1, s2, w, pos, out1, out2, sc_match, sc_mis, sc_gap);
+    walk_table<WALK_TABLE>(RowMajorCells{table, tpitch}, s1, s2, w, pos, out1, out2, sc_match, sc_mis, sc_gap);
+    if (threadIdx.x == 0) *out_len = pos[2];
+}
+
+// the same on a Smith-Waterman table: from the best cell (best[1], best[2] -- what nw_local_finish_kernel left on the device)
+// back to the first cell whose value is 0; out_len = number of alignment columns (0 when the best score is 0)
+__global__ void __launch_bounds__(256) nw_traceback_local_kernel(const int32_t* __restrict__ table, long long tpitch,
+                                                                 const uint8_t* __restrict__ s1, const uint8_t* __restrict__ s2,
+                                                                 const int32_t* __restrict__ best, uint8_t* out1, uint8_t* out2,
+                                                                 int* out_len, int sc_match, int sc_mis, int sc_gap)
+{
+    __shared__ WalkSmem w;
+    __shared__ int pos[4];
+    if (threadIdx.x == 0) { pos[0] = best[1]; pos[1] = best[2]; pos[2] = 0; pos[3] = 0; }
+    __syncthreads();
+    walk_table<WALK_LOCAL>(RowMajorCells{table, tpitch}, s1, s2, w, pos, out1, out2, sc_match, sc_mis, sc_gap);
     if (threadIdx.x == 0) *out_len = pos[2];
 }
 
@@ -749,7 +768,7 @@ __global__ void __launch_bounds__(TT_MAX_ROWS) nw_tile_trace_kernel(const TraceP
         int up[2][TT_B][TT_MAX_ROWS];      // fill: the blocks handed from row to row (row index last: no bank conflicts)
         WalkSmem walk;                     // then the walker's window
     } sm;
-    __shared__ int pos[3];
+    __shared__ int pos[4];
     const int tid = threadIdx.x;
     const int i = p.state[0], j = p.state[1], k0 = p.state[2];
     if ((i == 0 && j == 0) || p.state[3] != 0) return;
@@ -837,9 +856,9 @@ __global__ void __launch_bounds__(TT_MAX_ROWS) nw_tile_trace_kernel(const TraceP
     }
     // walk back inside the tile
     const long long clk1 = clock64();
-    if (tid == 0) { pos[0] = nr; pos[1] = wd; pos[2] = k0; }
+    if (tid == 0) { pos[0] = nr; pos[1] = wd; pos[2] = k0; pos[3] = 0; }
     __syncthreads();
-    walk_table<true>(TileCells{top, leftc, U, rp}, s1, p.s2 + i_top, sm.walk, pos, p.out1, p.out2, p.sc_match, p.sc_mis, p.sc_gap);
+    walk_table<WALK_TILE>(TileCells{top, leftc, U, rp}, s1, p.s2 + i_top, sm.walk, pos, p.out1, p.out2, p.sc_match, p.sc_mis, p.sc_gap);
     if (tid == 0) {
         p.state[0] = i_top + pos[0];
         p.state[1] = jl + pos[1];

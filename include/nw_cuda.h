@@ -186,7 +186,9 @@ int nw_plan_table_device(nw_plan* p, int32_t** d_table, int64_t* pitch);
  * produces an alignment).  Walks back from H[n2][n1] to H[0][0]: diagonal if H[i][j] == H[i-1][j-1] + (s1[j-1]==s2[i-1] ?
  * match : mismatch), else up if H[i][j] == H[i-1][j] + gap, else left.  a1 / a2 (HOST, capacity n1+n2 each) receive the
  * gapped s1 / s2 left to right, gap = 0; *len their common length.
- *   full-table plan (single part, table resident): walks the materialised table;
+ *   full-table plan (single part, table resident): walks the materialised table; on a local-alignment plan from the best
+ *   cell back to the first cell with H = 0 (the aligned segments end at nw_plan_best's cell and begin that many letters
+ *   earlier);
  *   boundary-mode plan: NO table -- the path is recovered tile by tile from the strip boundary rows the fill left in HBM
  *   (every tile between two checkpoint rows is recomputed from its exact top row and left column, then walked).
  * nw_plans_traceback does the same for the connected parts 0..nparts-1 of a column-strip pipeline on ONE device that

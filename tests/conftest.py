@@ -70,6 +70,8 @@ class Oracle:
         L.nw_oracle_score_ex.restype = i32
         L.nw_oracle_traceback_ex.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp]
         L.nw_oracle_traceback_ex.restype = i32
+        L.nw_oracle_traceback_local.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp]
+        L.nw_oracle_traceback_local.restype = i32
         L.nw_oracle_fnv1a64.argtypes = [vp, i64]
         L.nw_oracle_fnv1a64.restype = C.c_uint64
         L.nw_oracle_fnv1a64_col.argtypes = [vp, i64, i64]
@@ -139,6 +141,13 @@ class Oracle:
         a1 = np.empty(s1.size + s2.size + 1, dtype=np.int8)
         a2 = np.empty(s1.size + s2.size + 1, dtype=np.int8)
         n = self.L.nw_oracle_traceback_ex(self._p(s1), s1.size, self._p(s2), s2.size, m, x, g, a1.ctypes.data, a2.ctypes.data)
+        return a1[:n].copy(), a2[:n].copy()
+
+    def traceback_local(self, s1, s2, scoring):
+        m, x, g = scoring[:3]
+        a1 = np.empty(s1.size + s2.size + 1, dtype=np.int8)
+        a2 = np.empty(s1.size + s2.size + 1, dtype=np.int8)
+        n = self.L.nw_oracle_traceback_local(self._p(s1), s1.size, self._p(s2), s2.size, m, x, g, a1.ctypes.data, a2.ctypes.data)
         return a1[:n].copy(), a2[:n].copy()
 
     def fnv(self, a):

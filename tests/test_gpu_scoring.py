@@ -168,6 +168,21 @@ def test_local_plan_rows_per_lane_and_checkpoints(gpu, oracle, R):
             p.last_row()
 
 
+@pytest.mark.parametrize("sc", [(2, -1, -2, 1), (3, -3, -2, 1), (5, -4, -3, 1), (1, -1, 0, 1)])
+@pytest.mark.parametrize("shape", [(0, 5), (1, 1), (33, 31), (300, 1000), (2500, 2100), (129, 4097)])
+def test_local_traceback(gpu, oracle, sc, shape):
+    n1, n2 = shape
+    s1, s2 = synth_pair(700 + n1 + 3 * n2, n1, n2, 5)
+    with gpu.Plan(n1, n2, mode=gpu.NW_MODE_FULL, scoring=sc) as p:
+        p.upload(s1, s2)
+        p.run()
+        a1, a2 = p.traceback()
+        best, i, j = p.best()
+    b1, b2 = oracle.traceback_local(s1, s2, sc)
+    assert np.array_equal(a1, b1) and np.array_equal(a2, b2)
+    assert np.array_equal(a1[a1 != 0], s1[j - int((a1 != 0).sum()):j]) and np.array_equal(a2[a2 != 0], s2[i - int((a2 != 0).sum()):i])
+
+
 def test_local_tie_rule(gpu, oracle):
     # many equal maxima: identical short motifs scattered over both sequences
     rng = np.random.default_rng(8)

@@ -73,3 +73,17 @@ def test_local_properties(oracle, sc):
             assert (i, j) == (0, 0)
         # a local alignment is at least as good as the global one, and as any clamped global alignment of prefixes
         assert best >= max(0, int(oracle.fill_ex(s1, s2, sc[:3]).max()))
+
+
+@pytest.mark.parametrize("sc", [(2, -1, -2, 1), (3, -3, -2, 1), (1, -1, 0, 1)])
+def test_local_traceback_properties(oracle, sc):
+    rng = np.random.default_rng(23)
+    m, x, g = sc[:3]
+    for _ in range(5):
+        s1, s2 = synth_pair(int(rng.integers(1 << 30)), int(rng.integers(1, 250)), int(rng.integers(1, 250)), 5)
+        best, i, j = oracle.score_ex(s1, s2, sc)
+        a1, a2 = oracle.traceback_local(s1, s2, sc)
+        col = np.where((a1 == 0) | (a2 == 0), g, np.where(a1 == a2, m, x))
+        assert int(col.sum()) == best                           # the aligned segments score the best cell's value
+        n1, n2 = int((a1 != 0).sum()), int((a2 != 0).sum())     # ... and are substrings ending at the best cell
+        assert np.array_equal(a1[a1 != 0], s1[j - n1:j]) and np.array_equal(a2[a2 != 0], s2[i - n2:i])
