@@ -10,12 +10,19 @@ LIB    := $(PKG)/libnw_cuda.so
 SRCS   := $(PKG)/csrc/nw_cuda.cu
 HDRS   := $(wildcard $(PKG)/csrc/*.cuh) include/nw_cuda.h
 
-.PHONY: all lib driver oracle clean
-all: lib oracle driver
+.PHONY: all lib driver oracle clean check
+all: lib oracle driver check
 
 lib: $(LIB)
 $(LIB): $(SRCS) $(HDRS)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRCS)
+
+# the same library with every global-memory index of the strip kernels asserted (NW_ASSERT in csrc/nw_kernels.cuh):
+# the in-tree substitute for compute-sanitizer; tests/test_gpu_checked.py runs tools/sanity_small.py against it
+check: build/libnw_check.so
+build/libnw_check.so: $(SRCS) $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -DNW_CHECK=1 -shared -o $@ $(SRCS)
 
 oracle:
 	$(MAKE) -C oracle all REF=$(REF)

@@ -25,6 +25,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <limits.h>
+#ifdef NW_CHECK
+#include <cassert>
+#endif
 
 namespace nw {
 
@@ -115,6 +118,27 @@ struct StripParams {
                                  // ends, then clock64 (SM cycles) at the same two points -- the trace behind the start-up
                                  // lag numbers and the SM clock actually seen (nw_plan_strip_times); or nullptr
 };
+
+// ---- bounds-check build (`make check`: -DNW_CHECK) --------------------------------------------------------------------------
+// compute-sanitizer is closed on the GPU pool this was developed on, so the library carries its own index checks: every
+// global-memory index of the strip kernels is asserted against the allocation as nw_cuda.cu sizes it.  A failed assert
+// traps the kernel; the host call then fails with NW_ERR_CUDA.  tests/test_gpu_checked.py runs every kernel family on the
+// check build.  Compiled out of the product build.
+#ifdef NW_CHECK
+#define NW_ASSERT(c) assert(c)
+#else
+#define NW_ASSERT(c) ((void)0)
+#endif
+__device__ __forceinline__ void chk_brow(const StripParams& p, int s, long long j)      // word j of boundary row s
+{
+    NW_ASSERT(s >= 0 && s < max(p.nstrips, 1) && j >= 0 && j < p.pitch);
+}
+__device__ __forceinline__ void chk_row(const StripParams& p, int i) { NW_ASSERT(i >= 1 && i <= p.n2); }      // halo / rcol index
+__device__ __forceinline__ void chk_wq(const StripParams& p, int c) { NW_ASSERT(c >= -WQ_PAD && c < p.ncols + WQ_PADR); }
+__device__ __forceinline__ void chk_table(const StripParams& p, long long i, long long j)
+{
+    NW_ASSERT(i >= 0 && i <= p.n2 && j >= 0 && j < p.tpitch);
+}
 
 __device__ __forceinline__ unsigned long long global_ns()
 {
@@ -208,7 +232,10 @@ __device__ __forceinline__ void sweep32(int (&h)[R], int& dprev, const RowOperan
                 diag = h[r];
                 up = max(t, up);                               // ... , G[i-1][j])
                 h[r] = up;
-                if (FULL) trow[r][col + 1] = up + hoff[r] + gcol;   // H = G + g*(i + j)
+                if (FULL) {
+                    NW_ASSERT(col + 1 >= 1 && col + 1 <= ncols);
+                    trow[r][col + 1] = up + hoff[r] + gcol;   // H = G + g*(i + j)
+                }
             }
         }
         if (lane == 31) sout[k] = h[R - 1];
@@ -247,6 +274,7 @@ __device__ __forceinline__ void run_strip(const StripParams& p, const int s, con
                 int2 t;
                 SpinGuard sg;
                 do {
+                    chk_row(p, i);
                     t = p.halo_sys ? ld_tagged_sys(p.halo + i) : ld_tagged_gpu(p.halo + i);
                     if (t.x != p.epoch) __nanosleep(100);
                 } while (t.x != p.epoch && !sg.expired(p));
@@ -262,6 +290,7 @@ __device__ __forceinline__ void run_strip(const StripParams& p, const int s, con
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int i = i0 + 1 + r;
+            if (i >= 1) chk_table(p, i, ncols);
             trow[FULL ? r : 0] = (i >= 1) ? p.table + (long long)i * p.tpitch : p.dump;
             hoff[FULL ? r : 0] = p.gap * (i + p.jstart + 1);     // H = G + g*(i + jstart + col + 1)
             trow[FULL ? r : 0][0] = h[r] + p.gap * (i + p.jstart);   // left boundary column (serial.cpp:17 / mpi-vert.cpp:57-59)
@@ -274,6 +303,8 @@ __device__ __forceinline__ void run_strip(const StripParams& p, const int s, con
 
     // column operand window: W[0..63] holds columns [cb-32, cb+32) of the current 32-step block
     const uint32_t* wq = p.wq;
+    chk_wq(p, lane - 32);
+    chk_wq(p, 32 + lane);
     W[lane] = wq[lane - 32];
     W[lane + 32] = wq[lane];
     uint32_t wnext = wq[32 + lane];
@@ -281,7 +312,7 @@ __device__ __forceinline__ void run_strip(const StripParams& p, const int s, con
 
     // top boundary row: prefetched one block ahead
     int2 pre = make_int2(0, 0);
-    if (s > 0 && lane < ncols) pre = ld_tagged_gpu(tin + lane + 1);
+    if (s > 0 && lane < ncols) { chk_brow(p, s - 1, lane + 1); pre = ld_tagged_gpu(tin + lane + 1); }
     if (s == 0) sin[lane] = 0;
 
     const int nblocks = (ncols + 31 + 31) >> 5;     // steps t = 0 .. ncols+30
@@ -291,11 +322,13 @@ __device__ __forceinline__ void run_strip(const StripParams& p, const int s, con
             W[lane] = W[lane + 32];
             W[lane + 32] = wnext;
             int nc = cb + 32 + lane;
+            chk_wq(p, nc < ncols + WQ_PAD ? nc : ncols + WQ_PAD - 1);
             wnext = wq[nc < ncols + WQ_PAD ? nc : ncols + WQ_PAD - 1];
         }
         if (s > 0 && cb < ncols) {
             const int col = cb + lane;
             const bool need = col < ncols;
+            if (need) chk_brow(p, s - 1, col + 1);
             SpinGuard sg;
             while (!__all_sync(FULL_MASK, !need || pre.x == p.epoch)) {
                 __nanosleep(100);
@@ -303,7 +336,7 @@ __device__ __forceinline__ void run_strip(const StripParams& p, const int s, con
                 if (sg.expired_warp(p)) break;
             }
             sin[lane] = pre.y;
-            if (col + 32 < ncols) pre = ld_tagged_gpu(tin + col + 33);
+            if (col + 32 < ncols) { chk_brow(p, s - 1, col + 33); pre = ld_tagged_gpu(tin + col + 33); }
         }
         __syncwarp();
         if (cb >= 31 && cb + 31 < ncols)
@@ -313,7 +346,7 @@ __device__ __forceinline__ void run_strip(const StripParams& p, const int s, con
         __syncwarp();
         const int oc = cb - 31 + lane;               // column finished by lane 31 at step k = lane of this block
         const int ov = sout[lane];
-        if (oc >= 0 && oc < ncols) st_tagged_gpu(tout + oc + 1, p.epoch, ov);
+        if (oc >= 0 && oc < ncols) { chk_brow(p, s, oc + 1); st_tagged_gpu(tout + oc + 1, p.epoch, ov); }
     }
 
     // right boundary column of this lane's rows
@@ -322,6 +355,7 @@ __device__ __forceinline__ void run_strip(const StripParams& p, const int s, con
         for (int r = 0; r < R; ++r) {
             const int i = i0 + 1 + r;
             if (i >= 1) {
+                chk_row(p, i);
                 if (p.rcol_sys) st_tagged_sys(p.rcol + i, p.epoch, h[r]);
                 else st_tagged_gpu(p.rcol + i, p.epoch, h[r]);
             }

@@ -176,6 +176,8 @@ __device__ __forceinline__ void run_strip16l2(const StripParams& p, const int s,
         const int w = (c0 + fx + fskew) & 255;
         if (STAIR) {       // word by word: the cut may fall between the two (selects, no branch)
             const int ca = c0 + fx, cb2 = ca + 1;
+            if (ca < xcut) chk_wq(p, ca);
+            if (cb2 < xcut) chk_wq(p, cb2);
             const uint32_t* sa = (ca >= xcut) ? ((ca < xcut + 64) ? tail + (ca - xcut) : virt) : wq + ca;
             const uint32_t* sb = (cb2 >= xcut) ? ((cb2 < xcut + 64) ? tail + (cb2 - xcut) : virt) : wq + cb2;
             cp_async4_if(true, fdst + w, sa);
@@ -183,6 +185,8 @@ __device__ __forceinline__ void run_strip16l2(const StripParams& p, const int s,
             cp_async4_if(w < L2_MIRROR, fdst + 256 + w, sa);
             cp_async4_if(w < L2_MIRROR, fdst + 256 + w + 1, sb);
         } else {
+            chk_wq(p, c0 + fx);
+            chk_wq(p, c0 + fx + 1);
             cp_async8(fdst + w, wq + c0 + fx);
             cp_async8_if(w < L2_MIRROR, fdst + 256 + w, wq + c0 + fx);
         }
@@ -205,6 +209,8 @@ __device__ __forceinline__ void run_strip16l2(const StripParams& p, const int s,
 #pragma unroll
         for (int r = -1; r < R; ++r) {
             const int a = i_lo + 1 + r, b = i_hi + 1 + r;
+            if (a >= 1) chk_row(p, a);
+            if (b >= 1) chk_row(p, b);
             lo[r + 1] = (a >= 1) ? poll_tagged(p, p.halo + a, p.epoch, p.halo_sys).y : 0;
             hi[r + 1] = (b >= 1) ? poll_tagged(p, p.halo + b, p.epoch, p.halo_sys).y : 0;
             mn = min(mn, min(lo[r + 1], hi[r + 1]));
@@ -232,6 +238,7 @@ __device__ __forceinline__ void run_strip16l2(const StripParams& p, const int s,
     auto fetch_top = [&](int c0, int par) {
         // (strip 0 has no row above: no fetch.  Its "row above" used to be its own row a block ahead of its stores, i.e.
         //  words of an earlier fill that have long left L2 -- one DRAM round trip per block on the critical path.)
+        if (s > 0 && lane < 16 && c0 + 2 * lane <= clast) chk_brow(p, s - 1, c0 + 1 + 2 * lane + 1);
         cp_async16_cg_if(s > 0 && lane < 16 && c0 + 2 * lane <= clast, stag + (par << 5) + 2 * lane, tin + c0 + 1 + 2 * lane);
         cp_async_commit();
     };
@@ -255,6 +262,7 @@ __device__ __forceinline__ void run_strip16l2(const StripParams& p, const int s,
             // past the last column the row above is frozen and this strip's rows are too: any small value will do
             const bool need = (nb << 5) + lane <= clast;
             const int2* a = tin + (nb << 5) + lane + 1;
+            if (need) chk_brow(p, s - 1, (nb << 5) + lane + 1);
             SpinGuard sg;
 #if NW_L2_DBG & 1024
             const long long tw0 = clock64();
@@ -300,6 +308,7 @@ __device__ __forceinline__ void run_strip16l2(const StripParams& p, const int s,
                 if (!(NW_L2_DBG & 128)) fetch_top(cb + 32, (b & 1) ^ 1);
                 const int oc = cb - 32 - L2_SKEW + lane;
                 int2* const dst = ((unsigned)oc < (unsigned)ncols) ? tout + oc + 1 : dump;
+                chk_brow(p, s, dst - tout);
                 if (!(NW_L2_DBG & 256)) st_tagged_gpu(dst, p.epoch, ((int)so_prev[lane] >> 16) + pub_base);
             },
             [&] { if (!(NW_L2_DBG & 512)) fill(cb + 96); },
@@ -336,8 +345,10 @@ __device__ __forceinline__ void run_strip16l2(const StripParams& p, const int s,
     __syncwarp();
     {   // the last block's bottom row
         const int oc = ((nblocks - 1) << 5) - L2_SKEW + lane;
-        if (oc >= 0 && oc < ncols)
+        if (oc >= 0 && oc < ncols) {
+            chk_brow(p, s, oc + 1);
             st_tagged_gpu(tout + oc + 1, p.epoch, ((int)sout[(((nblocks - 1) & 1) << 5) + lane] >> 16) + pub_base);
+        }
     }
 
     if (p.times != nullptr && lane == 0) { p.times[4 * s + 1] = global_ns(); p.times[4 * s + 3] = (unsigned long long)clock64(); }
@@ -349,6 +360,8 @@ __device__ __forceinline__ void run_strip16l2(const StripParams& p, const int s,
             const int a = i_lo + 1 + r, b = i_hi + 1 + r;
             const int va = (int)(short)(h[r] & 0xffffu) + base, vb = ((int)h[r] >> 16) + base;
             // (a, b <= n2: rows below the table exist when the padding sits at the bottom)
+            if (a >= 1 && (!STAIR || a <= p.n2)) chk_row(p, a);
+            if (b >= 1 && (!STAIR || b <= p.n2)) chk_row(p, b);
             if (p.rcol_sys) {
                 if (a >= 1 && (!STAIR || a <= p.n2)) st_tagged_sys(p.rcol + a, p.epoch, va);
                 if (b >= 1 && (!STAIR || b <= p.n2)) st_tagged_sys(p.rcol + b, p.epoch, vb);

@@ -170,6 +170,8 @@ __device__ __forceinline__ void run_strip16(const StripParams& p, const int s, c
 #pragma unroll
         for (int r = -1; r < R; ++r) {
             const int a = i_lo + 1 + r, b = i_hi + 1 + r;
+            if (a >= 1) chk_row(p, a);
+            if (b >= 1) chk_row(p, b);
             lo[r + 1] = (a >= 1) ? poll_tagged(p, p.halo + a, p.epoch, p.halo_sys).y : 0;
             hi[r + 1] = (b >= 1) ? poll_tagged(p, p.halo + b, p.epoch, p.halo_sys).y : 0;
             mn = min(mn, min(lo[r + 1], hi[r + 1]));
@@ -185,9 +187,10 @@ __device__ __forceinline__ void run_strip16(const StripParams& p, const int s, c
     if (lane == 31) st_tagged_gpu(tout, p.epoch, ((int)h[R - 1] >> 16) + base);      // j = 0: the boundary column
 
     const uint32_t* wq = p.wq;
+    chk_wq(p, lane);
     uint32_t wnext = wq[lane];
     int2 pre = make_int2(0, 0);
-    if (s > 0 && lane < ncols) pre = ld_tagged_gpu(tin + lane + 1);
+    if (s > 0 && lane < ncols) { chk_brow(p, s - 1, lane + 1); pre = ld_tagged_gpu(tin + lane + 1); }
 
     const int nblocks = (ncols + 63 + 31) >> 5;          // the high half of lane 31 reaches column ncols-1 at t = ncols+62
     uint32_t scar = __shfl_sync(FULL_MASK, h[R - 1], src_lane);
@@ -208,11 +211,12 @@ __device__ __forceinline__ void run_strip16(const StripParams& p, const int s, c
                 const bool need = col < ncols;
                 SpinGuard sg;
                 while (!__all_sync(FULL_MASK, !need || pre.x == p.epoch)) {
+                    if (need) chk_brow(p, s - 1, col + 1);
                     if (need && pre.x != p.epoch) pre = ld_tagged_gpu(tin + col + 1);
                     if (sg.expired_warp(p)) break;
                 }
                 v = pre.y;
-                if (col + 32 < ncols) pre = ld_tagged_gpu(tin + col + 33);
+                if (col + 32 < ncols) { chk_brow(p, s - 1, col + 33); pre = ld_tagged_gpu(tin + col + 33); }
             }
             sin[lane] = (uint32_t)(v - base) & 0xffffu;
             if (b == 0 && p.times != nullptr && lane == 0) { p.times[4 * s] = global_ns(); p.times[4 * s + 2] = (unsigned long long)clock64(); }
@@ -225,7 +229,7 @@ __device__ __forceinline__ void run_strip16(const StripParams& p, const int s, c
         __syncwarp();
         {
             const int oc = cb - 63 + lane;               // column finished by the high half of lane 31 at step k = lane
-            if (oc >= 0 && oc < ncols) st_tagged_gpu(tout + oc + 1, p.epoch, ((int)sout[lane] >> 16) + base);
+            if (oc >= 0 && oc < ncols) { chk_brow(p, s, oc + 1); st_tagged_gpu(tout + oc + 1, p.epoch, ((int)sout[lane] >> 16) + base); }
         }
         if ((b & 31) == 31) {                            // re-base: keep the stored values small
             uint32_t mm = dprev;
@@ -366,6 +370,7 @@ __global__ void __launch_bounds__(256) nw_full16_kernel(const StripParams p)
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
                 const int c = cb - 96 + 32 * q + lane;
+                chk_wq(p, c);
                 const uint32_t w = wq[c];               // c >= -WQ_PAD always holds here (cb >= 32 * tile_blocks >= 64)
 #pragma unroll
                 for (int mm = 0; mm < 4; ++mm) ring[mm * RING_COPY_WORDS + ((c + mm) & 127)] = w;
@@ -432,6 +437,8 @@ __global__ void __launch_bounds__(256) nw_full16_kernel(const StripParams p)
                             const int L = L0 + u;
                             if (pos[u] >= 0) {
                                 int32_t* q = table + (long long)(row0 + L * R) * tpitch + (cb - L - 7 + pos[u]);
+                                NW_ASSERT(row0 + L * R >= 1 && row0 + L * R + R - 1 + 32 * R <= p.n2 && cb - L - 7 + pos[u] - 32 >= 0 &&
+                                          cb - L - 7 + pos[u] < tpitch);
                                 const int o = o0 + L - L * R - pos[u];
 #pragma unroll
                                 for (int r = 0; r < R; ++r) {
