@@ -778,7 +778,13 @@ struct TraceParams {
     uint8_t* out1;
     uint8_t* out2;
 };
-constexpr int TT_B = 8;            // columns per thread per block step
+#ifndef NW_TT_B
+#define NW_TT_B 8
+#endif
+#ifndef NW_TT_DBG
+#define NW_TT_DBG 0                // development only: bit mask of tile-fill ingredients to leave out (timing experiments)
+#endif
+constexpr int TT_B = NW_TT_B;      // columns per thread per block step
 constexpr int TT_MAX_ROWS = 512;   // strip rows (threads)
 
 struct TileCells {
@@ -852,7 +858,7 @@ __global__ void __launch_bounds__(TT_MAX_ROWS) nw_tile_trace_kernel(const TraceP
     const int nsteps = nq + nr - 1;
     int upn[TT_B];                      // row 0 reads the top boundary row from global memory: one block ahead
 #pragma unroll
-    for (int x = 0; x < TT_B; ++x) upn[x] = (r == 0 && x < wd) ? top[x + 1] : 0;
+    for (int x = 0; x < TT_B; ++x) upn[x] = (r == 0) ? top[min(x + 1, wd)] : 0;
     for (int t = 0; t < nsteps; ++t) {
         const int q = t - r;
         if (rowok && q >= 0 && q < nq) {
@@ -862,31 +868,34 @@ __global__ void __launch_bounds__(TT_MAX_ROWS) nw_tile_trace_kernel(const TraceP
 #pragma unroll
                 for (int x = 0; x < TT_B; ++x) {
                     up[x] = upn[x];
-                    upn[x] = (c0 + TT_B + x < wd) ? top[c0 + TT_B + x + 1] : 0;
+                    upn[x] = (NW_TT_DBG & 8) ? 0 : top[min(c0 + TT_B + x + 1, wd)];
                 }
             } else {
 #pragma unroll
-                for (int x = 0; x < TT_B; ++x) up[x] = sm.up[(t - 1) & 1][x][r - 1];
+                for (int x = 0; x < TT_B; ++x) up[x] = (NW_TT_DBG & 4) ? x : sm.up[(t - 1) & 1][x][r - 1];
             }
             uint8_t cs[TT_B];
 #pragma unroll
-            for (int x = 0; x < TT_B; ++x) cs[x] = (c0 + x < wd) ? s1[c0 + x] : 0;
+            for (int x = 0; x < TT_B; ++x) cs[x] = (NW_TT_DBG & 2) ? 0 : s1[min(c0 + x, wd - 1)];
             int32_t* const Ut = U + (long long)t * TT_B * rp + r;      // this thread's cells of this phase: coalesced over r
+            // No per-cell bound checks: the ragged last block computes up to TT_B - 1 cells past the tile's last column from
+            // clamped letters.  A cell only depends on cells of its own or smaller columns, so what is computed there never
+            // reaches a real cell, and the scratch has room for whole blocks.  (With a branch per cell the letter loads could
+            // not be hoisted out of it: 157 cycles per cell instead of ~20.)
 #pragma unroll
             for (int x = 0; x < TT_B; ++x) {
-                if (c0 + x < wd) {
-                    const int sub = (cs[x] == b2) ? p.sc_match : p.sc_mis;
-                    const int h = max(max(diag + sub, up[x] + g), left + g);
-                    Ut[(long long)x * rp] = h;
-                    diag = up[x];
-                    left = h;
-                    up[x] = h;
-                }
+                const int sub = (cs[x] == b2) ? p.sc_match : p.sc_mis;
+                const int h = max(max(diag + sub, up[x] + g), left + g);
+                if (!(NW_TT_DBG & 1)) Ut[(long long)x * rp] = h;
+                diag = up[x];
+                left = h;
+                up[x] = h;
             }
 #pragma unroll
-            for (int x = 0; x < TT_B; ++x) sm.up[t & 1][x][r] = up[x];
+            for (int x = 0; x < TT_B; ++x)
+                if (!(NW_TT_DBG & 4)) sm.up[t & 1][x][r] = up[x];
         }
-        __syncthreads();
+        if (!(NW_TT_DBG & 16)) __syncthreads();
     }
     // walk back inside the tile
     const long long clk1 = clock64();
