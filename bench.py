@@ -795,12 +795,13 @@ def batch_numbers(nw, torch, npairs, steps, device, seed=20240607):
     b.upload(p1.numpy(), p2.numpy())
     b.time(1)
     ms = b.time(steps)
+    out = torch.empty(npairs, dtype=torch.int32).pin_memory().numpy()
+    sc = b.run_host(p1.numpy(), p2.numpy(), out)            # chunked: copies, kernels and score read-backs overlap
     t0 = time.perf_counter()
     for _ in range(steps):
-        b.upload(p1.numpy(), p2.numpy())
-        b.run()
-        sc = b.scores()
+        sc = b.run_host(p1.numpy(), p2.numpy(), out)
     e2e_s = (time.perf_counter() - t0) / steps
+    sc = sc.copy()
     b.close()
     out = {"workload": f"batch of {npairs} independent pairs, 1000 x 1000 each (BASELINE.json configs[4] at 1/5 size)"
                        if npairs != 1000000 else "batch of 1M pairs, 1000 x 1000",

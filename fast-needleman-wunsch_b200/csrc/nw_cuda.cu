@@ -2245,10 +2245,14 @@ struct nw_batch {
     uint8_t code[256];
     BatchKernel kernel = nullptr;
     size_t smem = 0;
+    cudaStream_t copy_stream = nullptr;            // nw_batch_run_host: H2D of chunk c+1 while chunk c computes
+    std::vector<cudaEvent_t> chunk_ev;
     int sc_match = 1, sc_mis = 0, sc_gap = -1;     // nw_scoring (default: the reference's macros)
     int w_match() const { return std::max(sc_match - 2 * sc_gap, 0); }
     int w_mis() const { return std::max(sc_mis - 2 * sc_gap, 0); }
 };
+
+static int batch_scan(nw_batch* b);
 
 extern "C" int nw_batch_destroy(nw_batch* b)
 {
@@ -2260,6 +2264,8 @@ extern "C" int nw_batch_destroy(nw_batch* b)
         if (x) cudaFree(x);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
+    for (cudaEvent_t e : b->chunk_ev) cudaEventDestroy(e);
+    if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
     return NW_OK;
@@ -2400,16 +2406,17 @@ extern "C" int nw_batch_upload_device(nw_batch* b, const int8_t* d_S1, const int
     return batch_scan(b);
 }
 
-static int batch_enqueue(nw_batch* b)
+static int batch_enqueue(nw_batch* b, long long first = 0, long long count = -1)
 {
     if (!b->uploaded) return fail(NW_ERR_STATE, "nw_batch_upload has not been called");
-    if (b->npairs == 0) return NW_OK;
+    if (count < 0) count = b->npairs - first;
+    if (count == 0) return NW_OK;
     nw::BatchParams bp;
-    bp.S1 = b->S1;
-    bp.S2 = b->S2;
-    bp.scores = b->d_scores;
+    bp.S1 = b->S1 + first * b->len1;
+    bp.S2 = b->S2 + first * b->len2;
+    bp.scores = b->d_scores + first;
     bp.scratch = b->d_scratch;
-    bp.npairs = b->npairs;
+    bp.npairs = count;
     bp.scratch_pitch = b->scratch_pitch;
     bp.len1 = b->len1;
     bp.len2 = b->len2;
@@ -2420,9 +2427,97 @@ static int batch_enqueue(nw_batch* b)
     bp.w_mis = b->w_mis();
     bp.gap = b->sc_gap;
     memcpy(bp.code, b->code, 256);
-    b->kernel<<<b->ctas, b->warps * 32, b->smem, b->stream>>>(bp);
+    const int ctas = (int)std::max<long long>(1, std::min<long long>(b->ctas, (count + b->warps - 1) / b->warps));
+    b->kernel<<<ctas, b->warps * 32, b->smem, b->stream>>>(bp);
     CK(cudaGetLastError());
     b->ran = true;
+    return NW_OK;
+}
+
+// Host arrays in, host scores out, in chunks: the H2D copy of chunk c+1 (copy stream) overlaps the kernel of chunk c, and
+// every chunk's scores go home as soon as they exist.  The kernel is chosen from the alphabet of chunk 0; the alphabet of
+// every later chunk is scanned on the device as it arrives, and if one turns out to need another kernel (a fifth letter)
+// the whole batch is simply run again the plain way.
+extern "C" int nw_batch_run_host(nw_batch* b, const int8_t* S1, const int8_t* S2, int32_t* scores, int nchunks)
+{
+    if (!b) return fail(NW_ERR_ARG, "batch is NULL");
+    const size_t t1 = (size_t)b->npairs * (size_t)b->len1, t2 = (size_t)b->npairs * (size_t)b->len2;
+    if ((t1 && !S1) || (t2 && !S2) || (b->npairs && !scores)) return fail(NW_ERR_ARG, "NULL pointer");
+    if (b->npairs == 0) return NW_OK;
+    CK(cudaSetDevice(b->device));
+    if (nchunks < 1) nchunks = std::max(1, env_int("NW_CUDA_BATCH_CHUNKS", 8));
+    nchunks = (int)std::min<long long>(nchunks, b->npairs);
+    if (!b->d_S1) CK(cudaMalloc(&b->d_S1, std::max<size_t>(t1, 1)));
+    if (!b->d_S2) CK(cudaMalloc(&b->d_S2, std::max<size_t>(t2, 1)));
+    b->S1 = b->d_S1;
+    b->S2 = b->d_S2;
+    if (!b->copy_stream) CK(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+    while ((int)b->chunk_ev.size() < nchunks) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        b->chunk_ev.push_back(e);
+    }
+    CK(cudaStreamSynchronize(b->stream));      // (an earlier run may still read the buffers)
+    const long long per = (b->npairs + nchunks - 1) / nchunks;
+    auto range = [&](int c, long long* first, long long* count) {
+        *first = (long long)c * per;
+        *count = std::max<long long>(0, std::min<long long>(per, b->npairs - *first));
+    };
+    // every copy is enqueued now; the copy stream runs ahead of the kernels
+    for (int c = 0; c < nchunks; ++c) {
+        long long f, n;
+        range(c, &f, &n);
+        if (n > 0 && b->len1 > 0)
+            CK(cudaMemcpyAsync(b->d_S1 + f * b->len1, (const uint8_t*)S1 + f * b->len1, (size_t)(n * b->len1), cudaMemcpyHostToDevice, b->copy_stream));
+        if (n > 0 && b->len2 > 0)
+            CK(cudaMemcpyAsync(b->d_S2 + f * b->len2, (const uint8_t*)S2 + f * b->len2, (size_t)(n * b->len2), cudaMemcpyHostToDevice, b->copy_stream));
+        CK(cudaEventRecord(b->chunk_ev[c], b->copy_stream));
+    }
+    // chunk 0 decides the kernel
+    uint32_t bm0[8];
+    {
+        long long f, n;
+        range(0, &f, &n);
+        CK(cudaStreamWaitEvent(b->stream, b->chunk_ev[0], 0));
+        CK(cudaMemsetAsync(b->d_bitmap, 0, 8 * sizeof(uint32_t), b->stream));
+        if (n * b->len1 > 0) nw::nw_presence_kernel64<<<296, 256, 0, b->stream>>>(b->S1, n * b->len1, b->d_bitmap);
+        if (n * b->len2 > 0) nw::nw_presence_kernel64<<<296, 256, 0, b->stream>>>(b->S2, n * b->len2, b->d_bitmap);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(bm0, b->d_bitmap, sizeof bm0, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+        bool seen[256];
+        bitmap_to_seen(bm0, seen);
+        b->generic = !build_code(seen, b->code);
+        if (env_int("NW_CUDA_GENERIC", 0)) b->generic = true;
+        int rc = batch_pick_kernel(b);
+        if (rc) return rc;
+        b->uploaded = true;
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        long long f, n;
+        range(c, &f, &n);
+        if (n == 0) continue;
+        if (c > 0) {
+            CK(cudaStreamWaitEvent(b->stream, b->chunk_ev[c], 0));
+            if (n * b->len1 > 0) nw::nw_presence_kernel64<<<296, 256, 0, b->stream>>>(b->S1 + f * b->len1, n * b->len1, b->d_bitmap);
+            if (n * b->len2 > 0) nw::nw_presence_kernel64<<<296, 256, 0, b->stream>>>(b->S2 + f * b->len2, n * b->len2, b->d_bitmap);
+        }
+        int rc = batch_enqueue(b, f, n);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(scores + f, b->d_scores + f, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, b->stream));
+    }
+    uint32_t bm[8];
+    CK(cudaMemcpyAsync(bm, b->d_bitmap, sizeof bm, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    bool same = true;
+    for (int k = 0; k < 8; ++k) same = same && ((bm[k] & ~bm0[k]) == 0);
+    if (!same) {
+        // a later chunk brought letters chunk 0 did not have: the letter codes (or the kernel) may not fit them
+        int rc = batch_scan(b);       // the whole batch is on the device by now
+        if (rc == NW_OK) rc = batch_enqueue(b);
+        if (rc == NW_OK) rc = nw_batch_scores(b, scores);
+        return rc;
+    }
     return NW_OK;
 }
 
@@ -2486,6 +2581,14 @@ extern "C" int nw_cuda_batch_scores_scored(const int8_t* S1, const int8_t* S2, i
     nw_batch* b = nullptr;
     int rc = nw_batch_create(&b, device, npairs, len1, len2);
     if (rc == NW_OK && scoring) rc = nw_batch_set_scoring(b, scoring);
+    if (rc == NW_OK && npairs >= 4096 && !env_int("NW_CUDA_BATCH_NO_CHUNKS", 0)) {      // overlapped: copies, kernels, scores
+        rc = nw_batch_run_host(b, S1, S2, scores, 0);
+        char keep2[512];
+        memcpy(keep2, g_err, sizeof keep2);
+        nw_batch_destroy(b);
+        memcpy(g_err, keep2, sizeof keep2);
+        return rc;
+    }
     if (rc == NW_OK) rc = nw_batch_upload(b, S1, S2);
     if (rc == NW_OK) rc = nw_batch_run(b);
     if (rc == NW_OK) rc = nw_batch_scores(b, scores);

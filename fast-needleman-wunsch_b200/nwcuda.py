@@ -26,7 +26,7 @@ EXPORTS = [
     "nw_batch_create", "nw_batch_destroy", "nw_batch_upload", "nw_batch_upload_device", "nw_batch_run",
     "nw_batch_sync", "nw_batch_time", "nw_batch_scores", "nw_cuda_dpx_peak",
     "nw_cuda_fill_scored", "nw_cuda_score_scored", "nw_cuda_batch_scores_scored", "nw_plan_create_scored", "nw_plan_best",
-    "nw_batch_set_scoring", "nw_plans_traceback", "nw_cuda_align",
+    "nw_batch_set_scoring", "nw_plans_traceback", "nw_cuda_align", "nw_batch_run_host",
 ]
 
 
@@ -99,6 +99,7 @@ def lib():
                                       C.POINTER(Scoring)],
             "nw_plan_best": [vp, vp, vp, vp],
             "nw_batch_set_scoring": [vp, C.POINTER(Scoring)],
+            "nw_batch_run_host": [vp, vp, vp, vp, C.c_int],
             "nw_plans_traceback": [C.POINTER(vp), C.c_int, vp, vp, ip],
             "nw_cuda_align": [vp, i32, vp, i32, C.POINTER(Scoring), vp, vp, ip, ip],
         }
@@ -410,6 +411,16 @@ class Batch:
 
     def upload_device(self, d_S1_ptr, d_S2_ptr):
         _ck(lib().nw_batch_upload_device(self._h, d_S1_ptr, d_S2_ptr))
+
+    def run_host(self, S1, S2, out=None, nchunks=0):
+        """Host arrays in, host scores out, chunked so that copies and kernels overlap (nw_batch_run_host)."""
+        S1, S2 = _seq(S1), _seq(S2)
+        if S1.shape != (self.npairs, self.len1) or S2.shape != (self.npairs, self.len2):
+            raise ValueError("batch shape differs from the plan's")
+        if out is None:
+            out = np.empty(self.npairs, dtype=np.int32)
+        _ck(lib().nw_batch_run_host(self._h, _ptr(S1), _ptr(S2), out.ctypes.data if out.size else None, nchunks))
+        return out
 
     def run(self):
         _ck(lib().nw_batch_run(self._h))

@@ -222,6 +222,10 @@ int nw_batch_run(nw_batch* b);
 int nw_batch_sync(nw_batch* b);
 int nw_batch_time(nw_batch* b, int iters, float* ms_per_run);
 int nw_batch_scores(nw_batch* b, int32_t* scores /* HOST, npairs */);
+/* HOST arrays in, HOST scores out, in `nchunks` chunks (0 = NW_CUDA_BATCH_CHUNKS, default 8): the H2D copy of chunk c+1
+ * overlaps the kernel of chunk c and every chunk's scores leave as soon as they exist.  Pinned host memory makes the
+ * copies asynchronous; pageable memory works too (the copy of the next chunk then blocks the host while the GPU computes). */
+int nw_batch_run_host(nw_batch* b, const int8_t* S1, const int8_t* S2, int32_t* scores, int nchunks);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Roofline support: measured integer/DPX pipe rate of `device`.

@@ -229,6 +229,44 @@ def test_batch_scores(gpu, oracle, shape):
     assert np.array_equal(gpu.batch_scores(S1, S2), oracle.batch_scores(S1, S2))
 
 
+@pytest.mark.parametrize("shape", [(5000, 100, 90), (4100, 1000, 1000), (3, 50, 60), (4097, 31, 700)])
+@pytest.mark.parametrize("nchunks", [0, 1, 3, 8])
+def test_batch_run_host_chunked(gpu, oracle, shape, nchunks):
+    # nw_batch_run_host: H2D of chunk c+1 overlaps the kernel of chunk c; same scores as the plain path and the oracle
+    n, l1, l2 = shape
+    rng = np.random.default_rng(n + l1)
+    S1 = rng.integers(1, 5, size=(n, l1), dtype=np.int8)
+    S2 = rng.integers(1, 5, size=(n, l2), dtype=np.int8)
+    b = gpu.Batch(n, l1, l2)
+    try:
+        got = b.run_host(S1, S2, nchunks=nchunks)
+        again = b.run_host(S1, S2, nchunks=nchunks)
+    finally:
+        b.close()
+    want = gpu.batch_scores(S1[:64], S2[:64])
+    assert np.array_equal(got, again) and np.array_equal(got[:64], want)
+    idx = rng.choice(n, size=min(n, 40), replace=False)
+    assert np.array_equal(got[idx], oracle.batch_scores(S1[idx], S2[idx]))
+
+
+def test_batch_run_host_late_letter_falls_back(gpu, oracle):
+    # a fifth letter that appears only in the last chunk: the kernel chosen from chunk 0 does not fit, the batch is redone
+    rng = np.random.default_rng(77)
+    n, L = 4200, 120
+    S1 = rng.integers(1, 5, size=(n, L), dtype=np.int8)
+    S2 = rng.integers(1, 5, size=(n, L), dtype=np.int8)
+    S1[-3:, ::7] = 9
+    S2[-2:, ::5] = 9
+    b = gpu.Batch(n, L, L)
+    try:
+        got = b.run_host(S1, S2, nchunks=6)
+    finally:
+        b.close()
+    idx = np.r_[0:20, n - 20:n]
+    assert np.array_equal(got[idx], oracle.batch_scores(S1[idx], S2[idx]))
+    assert np.array_equal(gpu.batch_scores(S1, S2), got)          # the one-shot call takes the same path
+
+
 def test_batch_generic_alphabet(gpu, oracle):
     rng = np.random.default_rng(8)
     S1 = rng.integers(-100, 100, size=(40, 300), dtype=np.int8)
