@@ -19,6 +19,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <emmintrin.h>
@@ -1372,11 +1374,80 @@ extern "C" int nw_plan_last_col(nw_plan* p, int32_t* last_col)
 // at a few GB/s.  Instead the table goes device -> pinned staging (DMA at PCIe rate) -> destination (several host
 // threads), double-buffered so that the DMA of chunk k+1 overlaps the host copy of chunk k.
 namespace {
+// Persistent host threads for the staging -> table copies.  (Spawning and joining 16 std::threads per 32 MB chunk cost more
+// than the copy itself: 2 GB through 64 chunks took 64 ms, of which the DMA needs 40.)
+class CopyPool {
+public:
+    ~CopyPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_work_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    // runs job(0) .. job(n-1), job(0) on the calling thread; returns when all are done
+    void run(int n, const std::function<void(int)>& job)
+    {
+        if (n <= 1) {
+            job(0);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            while ((int)workers_.size() < n - 1) {
+                const int id = (int)workers_.size() + 1;
+                workers_.emplace_back([this, id] { loop(id); });
+            }
+            job_ = &job;
+            njobs_ = n;
+            remaining_ = n - 1;
+            ++generation_;
+        }
+        cv_work_.notify_all();
+        job(0);
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [this] { return remaining_ == 0; });
+        job_ = nullptr;
+    }
+
+private:
+    void loop(int id)
+    {
+        unsigned seen = 0;
+        for (;;) {
+            const std::function<void(int)>* job = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_work_.wait(lk, [&] { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+                if (id < njobs_) job = job_;
+            }
+            if (job) {
+                (*job)(id);
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--remaining_ == 0) cv_done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_work_, cv_done_;
+    const std::function<void(int)>* job_ = nullptr;
+    int njobs_ = 0, remaining_ = 0;
+    unsigned generation_ = 0;
+    bool stop_ = false;
+};
+
+constexpr int STAGE_SLOTS = 4;     // pinned staging buffers per device: up to three DMAs in flight behind the host copy
 struct Staging {
-    void* buf[2] = {nullptr, nullptr};
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    void* buf[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
     size_t bytes = 0;
     int device = -1;
+    CopyPool* pool = nullptr;      // (leaked at exit on purpose: joining threads in a static destructor is fragile)
 };
 Staging g_stages[64];              // one pair of pinned buffers per device: parts of a pipeline deliver concurrently
 std::mutex g_stage_mus[64];
@@ -1405,21 +1476,18 @@ void stream_copy(char* dst, const char* src, size_t n)
     if (n - 64 * blocks) memcpy(dst + 64 * blocks, src + 64 * blocks, n - 64 * blocks);
 }
 
-void parallel_memcpy(char* dst, const char* src, size_t n, int nthreads)
+void parallel_memcpy(CopyPool* pool, char* dst, const char* src, size_t n, int nthreads)
 {
-    if (n < (4u << 20) || nthreads <= 1) {
+    if (n < (4u << 20) || nthreads <= 1 || pool == nullptr) {
         stream_copy(dst, src, n);
         return;
     }
-    std::vector<std::thread> th;
     const size_t per = ((n / nthreads) + 4095) & ~(size_t)4095;
-    for (int t = 1; t < nthreads; ++t) {
-        const size_t off = per * t;
-        if (off >= n) break;
-        th.emplace_back([=] { stream_copy(dst + off, src + off, std::min(per, n - off)); });
-    }
-    stream_copy(dst, src, std::min(per, n));
-    for (auto& x : th) x.join();
+    const int njobs = (int)std::min<size_t>((size_t)nthreads, (n + per - 1) / per);
+    pool->run(njobs, [=](int t) {
+        const size_t off = per * (size_t)t;
+        if (off < n) stream_copy(dst + off, src + off, std::min(per, n - off));
+    });
 }
 
 bool host_pointer_is_pinned(const void* p)
@@ -1439,17 +1507,18 @@ static int ensure_staging(int device)       // caller holds g_stage_mus[device]
     const size_t chunk = (size_t)std::max(1, env_int("NW_CUDA_STAGE_MB", 32)) << 20;
     if (g_stage.bytes == chunk && g_stage.device == device) return NW_OK;
     CK(cudaSetDevice(device));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < STAGE_SLOTS; ++i) {
         if (g_stage.buf[i]) cudaFreeHost(g_stage.buf[i]);
         if (g_stage.ev[i]) cudaEventDestroy(g_stage.ev[i]);
         g_stage.buf[i] = nullptr;
         g_stage.ev[i] = nullptr;
     }
     g_stage.bytes = 0;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < STAGE_SLOTS; ++i) {
         CK(cudaHostAlloc(&g_stage.buf[i], chunk, cudaHostAllocDefault));
         CK(cudaEventCreateWithFlags(&g_stage.ev[i], cudaEventDisableTiming));
     }
+    if (!g_stage.pool) g_stage.pool = new CopyPool;
     g_stage.bytes = chunk;
     g_stage.device = device;
     return NW_OK;
@@ -1489,47 +1558,44 @@ static int staged_d2h_2d_locked(nw_plan* p, char* dst, size_t hpitch, const char
     // unit of work: a run of whole rows (or a byte range when the table is contiguous on both sides)
     const size_t total = flat ? width * rows : rows;
     const size_t step = flat ? chunk : std::max<size_t>(1, chunk / width);
+    // a ring of STAGE_SLOTS pinned buffers: DMAs are issued as far ahead as there are free slots, the host retires them in
+    // order with the persistent copy threads
     size_t done_issue = 0, done_copy = 0;
-    int slot = 0;
-    size_t pend_off[2] = {0, 0}, pend_n[2] = {0, 0};
-    bool pending[2] = {false, false};
+    size_t pend_off[STAGE_SLOTS], pend_n[STAGE_SLOTS];
+    int head = 0, tail = 0, inflight = 0;           // next slot to issue into / oldest slot in flight
     while (done_copy < total) {
-        if (done_issue < total && !pending[slot]) {
+        while (done_issue < total && inflight < STAGE_SLOTS) {
             const size_t n = std::min(step, total - done_issue);
-            if (flat) CK(cudaMemcpyAsync(g_stage.buf[slot], src + done_issue, n, cudaMemcpyDeviceToHost, cs));
-            else CK(cudaMemcpy2DAsync(g_stage.buf[slot], width, src + done_issue * dpitch, dpitch, width, n,
+            if (flat) CK(cudaMemcpyAsync(g_stage.buf[head], src + done_issue, n, cudaMemcpyDeviceToHost, cs));
+            else CK(cudaMemcpy2DAsync(g_stage.buf[head], width, src + done_issue * dpitch, dpitch, width, n,
                                       cudaMemcpyDeviceToHost, cs));
-            CK(cudaEventRecord(g_stage.ev[slot], cs));
-            pend_off[slot] = done_issue;
-            pend_n[slot] = n;
-            pending[slot] = true;
+            CK(cudaEventRecord(g_stage.ev[head], cs));
+            pend_off[head] = done_issue;
+            pend_n[head] = n;
             done_issue += n;
-            slot ^= 1;
-            if (done_issue < total && !pending[slot]) continue;      // keep two DMAs in flight
+            head = (head + 1) % STAGE_SLOTS;
+            ++inflight;
         }
-        // retire the older one
-        const int o = pending[slot] ? slot : slot ^ 1;
+        const int o = tail;
         CK(cudaEventSynchronize(g_stage.ev[o]));
-        if (flat) parallel_memcpy(dst + pend_off[o], (const char*)g_stage.buf[o], pend_n[o], nthreads);
+        if (flat) parallel_memcpy(g_stage.pool, dst + pend_off[o], (const char*)g_stage.buf[o], pend_n[o], nthreads);
         else {
             const char* sb = (const char*)g_stage.buf[o];
             const size_t r0 = pend_off[o], nr = pend_n[o];
-            if (nr * width < (4u << 20)) {
+            if (nr * width < (4u << 20) || nthreads <= 1) {
                 for (size_t r = 0; r < nr; ++r) stream_copy(dst + (r0 + r) * hpitch, sb + r * width, width);
             } else {
-                std::vector<std::thread> th;
                 const size_t per = (nr + nthreads - 1) / nthreads;
-                for (int t = 0; t < nthreads; ++t) {
-                    const size_t a = per * t, b = std::min(nr, a + per);
-                    if (a >= b) break;
-                    th.emplace_back([=] { for (size_t r = a; r < b; ++r) stream_copy(dst + (r0 + r) * hpitch, sb + r * width, width); });
-                }
-                for (auto& x : th) x.join();
+                const int njobs = (int)((nr + per - 1) / per);
+                g_stage.pool->run(njobs, [=](int t) {
+                    const size_t a = per * (size_t)t, b = std::min(nr, a + per);
+                    for (size_t r = a; r < b; ++r) stream_copy(dst + (r0 + r) * hpitch, sb + r * width, width);
+                });
             }
         }
         done_copy += pend_n[o];
-        pending[o] = false;
-        slot = o;
+        tail = (tail + 1) % STAGE_SLOTS;
+        --inflight;
     }
     return NW_OK;
 }
