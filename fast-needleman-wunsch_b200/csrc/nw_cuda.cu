@@ -1765,7 +1765,7 @@ extern "C" int nw_plans_traceback(nw_plan* const* parts, int nparts, int8_t* a1,
     int rc = NW_OK;
     auto body = [&]() -> int {
         CK(dev_alloc(dev, st, &d_out, 2 * cap));
-        CK(dev_alloc(dev, st, &d_s1, (size_t)std::max(p0->n1, 1)));
+        CK(dev_alloc(dev, st, &d_s1, (size_t)p0->n1 + 32));      // (+ padding: the tile kernel reads whole aligned words)
         CK(dev_alloc(dev, st, &d_scratch, sizeof(int32_t) * scratch_ints));
         CK(dev_alloc(dev, st, &d_state, 8 * sizeof(int)));
         CK(dev_alloc(dev, st, &d_parts, sizeof(nw::TracePart) * (size_t)nparts));

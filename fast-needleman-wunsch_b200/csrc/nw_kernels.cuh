@@ -751,7 +751,7 @@ __global__ void __launch_bounds__(256) nw_traceback_local_kernel(const int32_t* 
 //   1. fill the tile in H form from its exact top row and left column (blocked wavefront: thread r owns tile row r+1 and
 //      trails thread r-1 by one block of TT_B columns; neighbours exchange blocks through shared memory, one
 //      __syncthreads per block step) into a scratch table -- any alphabet, any linear scoring.  The scratch is
-//      PHASE-major (cell (r+1, c+1) at [((c / TT_B + r) * TT_B + c % TT_B) * rpitch + r]): at any instant the threads work on
+//      PHASE-major (cell (r+1, c+1) at [((c / TT_B + r) * rpitch + r) * TT_B + c % TT_B]): at any instant the threads work on
 //      different columns, and this is the layout in which their stores coalesce (row- or column-major scratch costs 32
 //      cache lines per store instruction and was 7x slower);
 //   2. walk back inside the scratch table (walk_table<true>) until the path reaches the tile's top row or left column;
@@ -798,7 +798,7 @@ struct TileCells {
         if (a == 0) return top[b];
         if (b == 0) return leftc[a];
         const int r = a - 1, c = b - 1;
-        return cells[(long long)(((c / TT_B) + r) * TT_B + (c % TT_B)) * rpitch + r];
+        return cells[((long long)((c / TT_B) + r) * rpitch + r) * TT_B + (c % TT_B)];
     }
 };
 
@@ -874,10 +874,22 @@ __global__ void __launch_bounds__(TT_MAX_ROWS) nw_tile_trace_kernel(const TraceP
 #pragma unroll
                 for (int x = 0; x < TT_B; ++x) up[x] = (NW_TT_DBG & 4) ? x : sm.up[(t - 1) & 1][x][r - 1];
             }
+            // the block's TT_B letters as ONE pair of aligned 8-byte loads + a funnel shift (byte loads get scheduled next to
+            // their uses and the cell chain then pays a load latency per cell).  Reads up to 15 bytes past the block: the
+            // caller pads s1; letters past the tile's last column only feed cells nobody reads.
             uint8_t cs[TT_B];
+            {
+                static_assert(TT_B <= 8, "one 64-bit word of letters per block");
+                const uintptr_t addr = (uintptr_t)(s1 + c0);
+                const unsigned long long* al = reinterpret_cast<const unsigned long long*>(addr & ~(uintptr_t)7);
+                const unsigned long long lo = (NW_TT_DBG & 2) ? 0ull : al[0], hi = (NW_TT_DBG & 2) ? 0ull : al[1];
+                const int sh = (int)(addr & 7) * 8;
+                const unsigned long long w = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
 #pragma unroll
-            for (int x = 0; x < TT_B; ++x) cs[x] = (NW_TT_DBG & 2) ? 0 : s1[min(c0 + x, wd - 1)];
-            int32_t* const Ut = U + (long long)t * TT_B * rp + r;      // this thread's cells of this phase: coalesced over r
+                for (int x = 0; x < TT_B; ++x) cs[x] = (uint8_t)(w >> (8 * x));
+            }
+            int32_t* const Ut = U + ((long long)t * rp + r) * TT_B;    // this thread's cells of this phase: TT_B consecutive ints,
+                                                                       // consecutive threads next to each other
             // No per-cell bound checks: the ragged last block computes up to TT_B - 1 cells past the tile's last column from
             // clamped letters.  A cell only depends on cells of its own or smaller columns, so what is computed there never
             // reaches a real cell, and the scratch has room for whole blocks.  (With a branch per cell the letter loads could
@@ -886,10 +898,14 @@ __global__ void __launch_bounds__(TT_MAX_ROWS) nw_tile_trace_kernel(const TraceP
             for (int x = 0; x < TT_B; ++x) {
                 const int sub = (cs[x] == b2) ? p.sc_match : p.sc_mis;
                 const int h = max(max(diag + sub, up[x] + g), left + g);
-                if (!(NW_TT_DBG & 1)) Ut[(long long)x * rp] = h;
                 diag = up[x];
                 left = h;
                 up[x] = h;
+            }
+            if (!(NW_TT_DBG & 1)) {
+                static_assert(TT_B % 4 == 0, "vector stores of the block");
+#pragma unroll
+                for (int x = 0; x < TT_B; x += 4) *reinterpret_cast<int4*>(Ut + x) = make_int4(up[x], up[x + 1], up[x + 2], up[x + 3]);
             }
 #pragma unroll
             for (int x = 0; x < TT_B; ++x)
