@@ -1867,9 +1867,13 @@ extern "C" int nw_cuda_align(const int8_t* s1, int32_t n1, const int8_t* s2, int
     tr.mark("align: create parts");
     for (int g = 0; g < P && rc == NW_OK; ++g) rc = nw_plan_upload(parts[g], s1, s2);
     tr.mark("align: upload");
+    // One device, P cooperative kernels: part g polls part g-1's right column, exactly like a part on another GPU would, so
+    // consecutive parts may be resident together -- part g then trails part g-1 by one part width instead of by a whole
+    // start-up ramp of the strip chain.  A window of W parts is in flight (part g waits for part g-W to finish); parts
+    // finish in order, so the oldest unfinished part is always resident and nothing can deadlock.
+    const int W = std::max(1, env_int("NW_CUDA_ALIGN_WINDOW", 8));
     for (int g = 0; g < P && rc == NW_OK; ++g) {
-        // one device: part g+1 polls part g's right column, so it must not occupy the SMs before part g is done
-        if (g > 0 && cudaStreamWaitEvent(parts[g]->stream, parts[g - 1]->ev1, 0) != cudaSuccess) rc = fail(NW_ERR_CUDA, "cudaStreamWaitEvent failed");
+        if (g >= W && cudaStreamWaitEvent(parts[g]->stream, parts[g - W]->ev1, 0) != cudaSuccess) rc = fail(NW_ERR_CUDA, "cudaStreamWaitEvent failed");
         if (rc == NW_OK) rc = nw_plan_run(parts[g]);
     }
     if (rc == NW_OK && score) rc = nw_plan_score(parts[(size_t)P - 1], score);
