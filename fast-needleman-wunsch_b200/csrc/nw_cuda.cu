@@ -251,6 +251,9 @@ int parse_scoring(const nw_scoring* in, int32_t n1, int32_t n2, Scoring* out)
         sc.match = in->match; sc.mismatch = in->mismatch; sc.gap = in->gap; sc.local = in->local;
     }
     if (sc.local && sc.gap > 0) return fail(NW_ERR_ARG, "local alignment needs gap <= 0 (got %d)", sc.gap);
+    if (sc.local && (long long)std::max(sc.match, 0) * std::min(n1, n2) >= (1LL << 27))     // (the kernel packs H * 8 + row)
+        return fail(NW_ERR_ARG, "scores (%d, %d, %d) overflow the local kernel's best-cell key on a %d x %d table", sc.match,
+                    sc.mismatch, sc.gap, n1, n2);
     long long a = std::max({std::llabs((long long)sc.match), std::llabs((long long)sc.mismatch), std::llabs((long long)sc.gap)});
     a = std::max(a, 2 * std::llabs((long long)sc.gap) + std::max(std::llabs((long long)sc.match), std::llabs((long long)sc.mismatch)));
     if (a * ((long long)n1 + n2 + 2) >= (1LL << 30))

@@ -9,7 +9,7 @@
 //     t = VIADDMNMX.RELU(diag, s, E_left)     -- __viaddmax_s32_relu: max(diag + s, left + gap, 0)
 //     H = VIADDMNMX(H_up, gap, t)             -- max(up + gap, t); the only op on the row-to-row chain
 //     E = H + gap
-// plus one VIMNMX per cell for the running best; the position is taken on a (rare) branch when a lane's best improves.
+// plus LEA + VIMNMX per cell for the running best as a key (H * 8 + 7 - row), and four selects per step -- no branch.
 // Decomposition, hand-off through tagged boundary rows and the persistent cooperative grid are those of nw_strip_kernel;
 // single part only (no halo / right column).  Virtual rows (padding above table row 1) get a hugely negative substitution
 // score, so with gap <= 0 they stay 0 like the first row.
@@ -35,7 +35,9 @@ __device__ __forceinline__ void sweep_local(int (&h)[R], int (&e)[R], int& dprev
         if (!PRED || (col >= 0 && col < ncols)) {
             int diag = dprev;
             dprev = up;
-            int m = 0;
+            // running best without a branch (a data-dependent branch inside the unrolled sweep makes the compiler fence every
+            // later shuffle): key = H * 8 + (7 - r), so the maximum key is the largest H of the step with the smallest row
+            int mk = 0;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int w = (rowb[r] == cop) ? wm : wx[r];
@@ -45,15 +47,13 @@ __device__ __forceinline__ void sweep_local(int (&h)[R], int (&e)[R], int& dprev
                 h[r] = up;
                 e[r] = up + gap;
                 if (FULL) trow[r][col + 1] = up;
-                m = max(m, up);
+                mk = max(mk, up * 8 + (7 - r));
             }
-            if (m > best) {       // first visit of a new maximum: columns ascend within a lane, rows ascend within a step
-                best = m;
-                bj = col + 1;
-#pragma unroll
-                for (int r = R - 1; r >= 0; --r)
-                    if (h[r] == m) bi = i_first + r;
-            }
+            const int mh = mk >> 3;
+            const bool upd = mh > best;       // strictly greater: the first column of a new maximum stays
+            best = upd ? mh : best;
+            bj = upd ? col + 1 : bj;
+            bi = upd ? i_first + 7 - (mk & 7) : bi;
         }
         if (lane == 31) sout[k] = h[R - 1];
     }
