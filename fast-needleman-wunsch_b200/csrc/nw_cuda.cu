@@ -1865,6 +1865,7 @@ extern "C" int nw_cuda_align(const int8_t* s1, int32_t n1, const int8_t* s2, int
     for (int g = 0; g < P && rc == NW_OK; ++g) {
         rc = plan_create_internal(&parts[g], 0, n1, n2, NW_MODE_BOUNDARY, g, P, g == 0 ? nullptr : &tune, false, sc, true);
         if (rc == NW_OK && g == 0) tune.rows_per_lane = parts[0]->R_req = parts[0]->R;     // every part: the same strip height
+        if (g < 3) tr.mark(g == 0 ? "align:   part 0 created" : "align:   next part created");
     }
     for (int g = 0; g + 1 < P && rc == NW_OK; ++g) rc = nw_plan_connect(parts[g], parts[g + 1]);
     tr.mark("align: create parts");
